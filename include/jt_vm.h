@@ -1,0 +1,157 @@
+/* jt_vm.h -- C ABI of libjt_vm.so, the B200 (sm_100a) implementation of the
+ * TensoRF-VM volume-rendering hot path of Nemo1999/Joint-TensoRF.
+ *
+ * The reference has no FFI: its operator boundary is the Python class
+ * `model.tensorf_repr.BAT_VMSplit` (bateRF.py:7, batBase.py:12, tensorBase.py:374,
+ * tensoRF.py:145) selected at model/tensorf.py:375. Each entry point below names
+ * the reference method / ATen call sequence it replaces; the Python module
+ * `joint_tensorf_b200.B200_VMSplit` binds them with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name starts with `h_` (host);
+ *  - all tensors are fp32 unless stated; `stream` is the CUDA stream to launch on;
+ *  - functions never allocate, never synchronise, never touch another stream;
+ *  - sample counts that are only known on the device are passed as `n_dev`
+ *    (device int*) together with `n_max` (host upper bound used to size grids);
+ *    if `n_dev` is NULL, `n_max` is the count;
+ *  - return 0 (JT_OK) or a negative error code, see jt_strerror().
+ *
+ * Layouts
+ *  - VM factors are channel-last: plane i is [H_i][W_i][C_i], line i is [L_i][C_i]
+ *    (the physical layout of a torch [1,C,H,W] tensor in channels_last format);
+ *    h_factors = {plane0, plane1, plane2, line0, line1, line2};
+ *    h_dims    = {H0,H1,H2, W0,W1,W2, L0,L1,L2, C0,C1,C2}; C_i % 4 == 0.
+ *    Plane i is sampled at (x = u[mat0_i] -> W axis, y = u[mat1_i] -> H axis) with
+ *    matMode = [[0,1],[0,2],[1,2]], line i at u[vecMode_i], vecMode = [2,1,0]
+ *    (tensorBase.py:405-406).
+ *  - h_geom    = {aabb0[3], aabb1[3], invaabbSize[3], stepSize, near, far} (12 floats),
+ *    computed with torch exactly as tensorBase.py:477-488 does.
+ *  - a compacted sample j carries samp[j] = float4 (u_x, u_y, u_z, t): normalised
+ *    coordinates (tensorBase.py:502-503) and its depth along the ray.
+ */
+#ifndef JT_VM_H_
+#define JT_VM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* ---- library ----------------------------------------------------------- */
+const char* jt_strerror(int code);
+int jt_version(void);            /* ABI version, bumped on any signature change */
+/* number of kernel launches issued through this library since load (for bench.py) */
+long long jt_launch_count(void);
+
+/* ---- K1: ray marching -------------------------------------------------- */
+/* TensorBase.sample_ray (tensorBase.py:572-612) / sample_ray_ndc (554-571) with the
+ * alpha-mask cull of batBase.py:76-82 folded in; dense outputs as the reference
+ * returns them: pts [N,S,3], z [N,S], valid [N,S] (uint8).
+ * aux: metric rays -> per-ray jitter [N] or NULL (is_train False);
+ *      NDC rays    -> depth table [S] (torch.linspace (+jitter)), required.
+ * mask_bits: bit-packed AlphaGridMask volume or NULL; h_mask_dims = {W,H,D};
+ * h_mask_geom = {mask_aabb0[3], invgridSize[3]} (tensorBase.py:85-86). */
+int jt_sample_ray_dense(const float* rays_o, const float* rays_d, const float* aux, int ndc, int n_rays,
+                        int n_samples, const float* h_geom, const uint32_t* mask_bits, const int* h_mask_dims,
+                        const float* h_mask_geom, float* pts, float* z, uint8_t* valid, cudaStream_t stream);
+
+/* Same sampler, compacted: replaces sample_ray + the boolean-mask indexing
+ * xyz_sampled[ray_valid] (batBase.py:104-120). Outputs, ray-major and depth-ordered:
+ * ray_off [N+1] (exclusive scan of per-ray valid counts; ray_off[N] = V),
+ * sidx [V] = ray*S + k, samp [V] float4, dist [V] = z[k+1]-z[k] (0 for k = S-1,
+ * batBase.py:69; x |ray_dir| for NDC rays, batBase.py:63-65). ray_cnt [N] is scratch.
+ * Capacity of sidx/samp/dist must be N*S. */
+int jt_march_compact(const float* rays_o, const float* rays_d, const float* aux, int ndc, int n_rays,
+                     int n_samples, const float* h_geom, const uint32_t* mask_bits, const int* h_mask_dims,
+                     const float* h_mask_geom, int* ray_cnt, int* ray_off, int* sidx, float* samp, float* dist,
+                     cudaStream_t stream);
+
+int jt_exclusive_scan(const int* cnt, int* off, int n, cudaStream_t stream);
+
+/* ---- K2: VM plane x line interpolation --------------------------------- */
+/* app = 0: BAT_VMSplit.compute_densityfeature (bateRF.py:41-94, tensoRF.py:230-251):
+ *          out[e] = sum_i sum_c plane_i,c(u) * line_i,c(u)                       out [n]
+ * app = 1: gather part of compute_appfeature (bateRF.py:97-128, tensoRF.py:254-268):
+ *          out[e][off_i + c] = plane_i,c(u) * line_i,c(u)                        out [n][sum C]
+ * Element e reads samp[slot ? slot[e] : e]. */
+int jt_vm_gather_fwd(int app, const void* const* h_factors, const int* h_dims, const float* samp,
+                     const int* slot, const int* n_dev, int n_max, float* out, cudaStream_t stream);
+
+/* Backward of jt_vm_gather_fwd (replaces grid_sampler_2d_backward x12): scatters
+ * into the channel-last gradient buffers h_factor_grads (same order/shape as
+ * h_factors, pre-zeroed by the caller) and writes dL/du to dsamp (float4 per sample
+ * slot, xyz used; accumulate = 0 store, 1 add). gin: app=0 [n], app=1 [n][sum C]. */
+int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,
+                     const float* samp, const int* slot, const int* n_dev, int n_max, const float* gin,
+                     float* dsamp, int accumulate, cudaStream_t stream);
+
+/* ---- K3: basis_mat + shading head (strict fp32 path) -------------------- */
+/* Y[m][0..N) = act(sum_k X[m][k] * W(n,k) + bias[n]) (* (mask[m][n] > 0)); W(n,k) =
+ * W[n*ldw+k] (torch Linear weight) or W[k*ldw+n] if w_kn. act: 0 none, 1 relu,
+ * 2 sigmoid. Replaces basis_mat (tensoRF.py:156,270) and the Linear layers of
+ * MLPRender_Fea / _WeakView (tensorBase.py:109-111,189-191) and their input grads. */
+int jt_gemm_nt(const float* X, int ldx, const float* W, int ldw, int w_kn, const float* bias, float* Y, int ldy,
+               const float* mask, int ldm, const int* m_dev, int m_max, int N, int K, int act,
+               cudaStream_t stream);
+/* dW[n][k] += sum_m dY[m][n] X[m][k]; db[n] += sum_m dY[m][n] (weight gradients). */
+int jt_gemm_tn(const float* dY, int ldy, const float* X, int ldx, const int* m_dev, int m_max, int N, int K,
+               float* dW, int ldw, float* db, cudaStream_t stream);
+/* positional_encoding (tensorBase.py:43-55) + the input concatenation of
+ * MLPRender_Fea.forward (tensorBase.py:116-122; mode 0) or MLPRender_Fea_WeakView
+ * (tensorBase.py:198-206; mode 1, view encoding goes to out2). bwd = 1 maps din
+ * (gradient of the encoded row) back to dfeat (written to `out`). View directions
+ * are rays_d[sidx[aidx[a]] / n_samples], normalised if normalize_dir (NDC). */
+int jt_pe_encode(int bwd, int app_dim, int fea_pe, int view_pe, int mode, float fea_progress,
+                 float view_progress, int n_samples, int normalize_dir, const float* feat, int ldf,
+                 const int* aidx, const int* sidx, const float* rays_d, const int* n_dev, int n_max, float* out,
+                 int ldo, float* out2, int ldo2, const float* din, int ldi, cudaStream_t stream);
+/* SHRender (tensorBase.py:68-72) with eval_sh_bases(2, .) (sh.py:88-113). */
+int jt_sh_shade(int bwd, const float* feat, int ldf, const int* aidx, const int* sidx, const float* rays_d,
+                int n_samples, int normalize_dir, const int* n_dev, int n_max, float* rgb, const float* dout,
+                float* dfeat, int ldd, cudaStream_t stream);
+
+/* ---- K4: alpha compositing --------------------------------------------- */
+/* feature2density (tensorBase.py:696-700; act 0 softplus, 1 relu) + raw2alpha
+ * (tensorBase.py:57-65) over the compacted samples of each ray, then the app_mask
+ * selection weight > thres (batBase.py:127) compacted: app_off [N+1], aidx [A] ->
+ * sample slot, app_of [V] -> appearance slot or -1. Also per ray acc = sum w and
+ * wz = sum w*t. */
+int jt_alpha_fwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist, const float* samp,
+                 float density_shift, int act, float distance_scale, float thres, float* weight, float* trans,
+                 float* acc, float* wz, int* app_cnt, int* app_off, int* aidx, int* app_of, cudaStream_t stream);
+/* batBase.py:142-165: rgb_map = clamp(sum w*rgb (+ 1-acc if white_bg), 0, 1);
+ * depth = sum w*t + (1-acc)*ray_dir_z + depth_bias (depth_bias = -near + 0.05);
+ * opacity = acc. rgb_pre keeps the un-clamped colour for the backward pass.
+ * Per-sample colours `rgb` and their gradients `dout` are [A][4] (xyz used). */
+int jt_composite_fwd(const int* app_off, int n_rays, const int* aidx, const float* weight, const float* rgb,
+                     const float* acc, const float* wz, const float* rays_d, int white_bg, float depth_bias,
+                     float* rgb_pre, float* rgb_map, float* depth, float* opacity, cudaStream_t stream);
+/* autograd of composite + raw2alpha + feature2density as one reverse scan per ray:
+ * (g_rgb [N,3], g_acc [N] or NULL) -> dout [A,3] (gradient at the shading head's
+ * pre-activation; shade_act 0 none, 1 sigmoid, 2 relu), dsig [V] (gradient of the
+ * density feature), dnorm [N] or NULL (NDC: dL/d|ray_dir| * |ray_dir|). */
+int jt_render_bwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist, const float* weight,
+                  const float* trans, const int* app_of, const float* rgb, const float* rgb_pre,
+                  const float* g_rgb, const float* g_acc, float density_shift, int act, float distance_scale,
+                  int white_bg, int shade_act, float* dout, float* dsig, float* dnorm, cudaStream_t stream);
+/* dL/du per sample -> dL/d rays_o, dL/d rays_d (pts = o + d*t, normalize_coord). */
+int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* dsamp, const float* rays_d,
+               const float* dnorm, const float* h_inv, float* d_o, float* d_d, cudaStream_t stream);
+
+/* ---- K5: separable blur ------------------------------------------------ */
+/* BAT_VMSplit.convolute_plane / convolute_line (bateRF.py:8-39) on a channel-last
+ * [H][W][C] array: replicate-padded cross-correlation with `taps` [ntaps] (device,
+ * odd) along W (axes bit 0) and/or H (bit 1); adjoint = 1 applies the transposed
+ * operator (backward pass). tmp [H][W][C] is needed when axes == 3. */
+int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* taps, int ntaps,
+               int axes, int adjoint, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JT_VM_H_ */

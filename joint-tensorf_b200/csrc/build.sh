@@ -1,0 +1,8 @@
+#!/bin/bash
+# Build libjt_vm.so for sm_100a (B200) in-tree. Usage: build.sh [extra nvcc flags]
+set -e
+cd "$(dirname "$0")"
+SRCS="lib.cu march.cu vm_gather.cu composite.cu shade.cu blur.cu"
+[ -f shade_tc.cu ] && SRCS="$SRCS shade_tc.cu"
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+     -Xcompiler -fPIC -shared -Xptxas -v "$@" -o libjt_vm.so $SRCS

@@ -1,0 +1,328 @@
+// K4 -- density activation, raw2alpha (transmittance scan), appearance-sample
+// selection + compaction, front-to-back compositing, and their backward pass
+// as a reverse scan.
+//
+// Replaces reference feature2density (tensorBase.py:696-700), raw2alpha
+// (tensorBase.py:57-65), the app_mask selection + boolean indexing
+// (batBase.py:127-139) and the accumulation / background / clamp / depth block
+// (batBase.py:142-165), plus the autograd of all of them.
+//
+// One warp owns one ray and walks its compacted valid samples 32 at a time;
+// the running transmittance is a warp product-scan with a carry. Invalid
+// samples have sigma = 0 in the reference, i.e. alpha = 0 and a factor
+// 1 - 0 + 1e-10 == 1.0f in the cumprod, so skipping them is exact.
+#include "jt_common.cuh"
+#include "../../include/jt_vm.h"
+
+namespace jt {
+
+__device__ __forceinline__ float density_act(float x, int act) {
+    // act 0: softplus (beta 1, threshold 20; ATen softplus), act 1: relu. x already includes the shift.
+    if (act == 0) return x > 20.0f ? x : log1pf(expf(x));
+    return fmaxf(x, 0.0f);
+}
+__device__ __forceinline__ float density_act_grad(float x, int act) {
+    if (act == 0) {
+        if (x > 20.0f) return 1.0f;
+        float z = expf(x);
+        return z / (z + 1.0f);
+    }
+    return x > 0.0f ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------ forward, pass A
+// per ray: sigma -> alpha -> T (exclusive product scan) -> weight; accumulates acc
+// and sum(w*z); counts appearance samples (w > thres).
+__global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ off, int n_rays,
+                                                        const float* __restrict__ sigfeat,
+                                                        const float* __restrict__ dist,
+                                                        const float4* __restrict__ samp, float shift, int act,
+                                                        float dscale, float thres, float* __restrict__ weight,
+                                                        float* __restrict__ trans, float* __restrict__ acc_out,
+                                                        float* __restrict__ wz_out, int* __restrict__ app_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rays; r += nwarps) {
+        const int b = off[r], e = off[r + 1];
+        float carry = 1.0f, acc = 0.f, wz = 0.f;
+        int cnt = 0;
+        for (int j0 = b; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            float q = 1.0f, alpha = 0.f, z = 0.f;
+            if (j < e) {
+                float sigma = density_act(sigfeat[j] + shift, act);
+                alpha = 1.0f - expf(-sigma * (dist[j] * dscale));
+                q = 1.0f - alpha + 1e-10f;
+                z = samp[j].w;
+            }
+            float p = q;                                     // inclusive product scan over the warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float v = __shfl_up_sync(0xffffffffu, p, o);
+                if (lane >= o) p *= v;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, p, 1);
+            if (lane == 0) excl = 1.0f;
+            const float T = carry * excl;
+            const float w = alpha * T;
+            if (j < e) {
+                weight[j] = w;
+                trans[j] = T;
+                acc += w;
+                wz += w * z;
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, (j < e) && (w > thres)));
+            carry *= __shfl_sync(0xffffffffu, p, 31);
+        }
+        acc = warp_sum(acc);
+        wz = warp_sum(wz);
+        if (lane == 0) { acc_out[r] = acc; wz_out[r] = wz; app_cnt[r] = cnt; }
+    }
+}
+
+// ------------------------------------------------------------------ forward, pass B
+// appearance compaction: aidx[a] = sample slot j, app_of[j] = a (or -1).
+__global__ void __launch_bounds__(256) app_fill_kernel(const int* __restrict__ off, const int* __restrict__ aoff,
+                                                       int n_rays, const float* __restrict__ weight, float thres,
+                                                       int* __restrict__ aidx, int* __restrict__ app_of) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rays; r += nwarps) {
+        const int b = off[r], e = off[r + 1];
+        int base = aoff[r];
+        for (int j0 = b; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            const bool ok = (j < e) && (weight[j] > thres);
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (j < e) {
+                int a = ok ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+                app_of[j] = a;
+                if (ok) aidx[a] = j;
+            }
+            base += __popc(m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward, pass C
+// rgb_map = sum w*rgb (+ 1-acc if white) clamped; depth; opacity.
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const int* __restrict__ aoff, int n_rays,
+                                                            const int* __restrict__ aidx,
+                                                            const float* __restrict__ weight,
+                                                            const float* __restrict__ rgb,
+                                                            const float* __restrict__ acc_in,
+                                                            const float* __restrict__ wz_in,
+                                                            const float* __restrict__ rays_d, int white_bg,
+                                                            float depth_bias, float* __restrict__ rgb_pre,
+                                                            float* __restrict__ rgb_map, float* __restrict__ depth,
+                                                            float* __restrict__ opacity) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rays; r += nwarps) {
+        const int b = aoff[r], e = aoff[r + 1];
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        for (int a = b + lane; a < e; a += 32) {
+            const float w = weight[aidx[a]];
+            c0 += w * rgb[4 * (size_t)a + 0];
+            c1 += w * rgb[4 * (size_t)a + 1];
+            c2 += w * rgb[4 * (size_t)a + 2];
+        }
+        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+        if (lane == 0) {
+            const float acc = acc_in[r];
+            const float bg = white_bg ? (1.0f - acc) : 0.0f;
+            c0 += bg; c1 += bg; c2 += bg;
+            rgb_pre[3 * r + 0] = c0; rgb_pre[3 * r + 1] = c1; rgb_pre[3 * r + 2] = c2;
+            rgb_map[3 * r + 0] = fminf(fmaxf(c0, 0.f), 1.f);
+            rgb_map[3 * r + 1] = fminf(fmaxf(c1, 0.f), 1.f);
+            rgb_map[3 * r + 2] = fminf(fmaxf(c2, 0.f), 1.f);
+            depth[r] = wz_in[r] + (1.0f - acc) * rays_d[3 * r + 2] + depth_bias;   // - near + 0.05
+            opacity[r] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward
+// Reverse walk over a ray's valid samples: d rgb_map / d opacity ->
+//   dout[a]   = dL/d(pre-activation of the shading head)   (shade_act folds sigmoid / relu')
+//   dsig[j]   = dL/d sigma_feature
+//   dnorm[r]  = dL/d |ray_dir|   (NDC rays only: dists are scaled by the norm)
+// with S_j = sum_{i>j} dL/dw_i * w_i  (suffix sum) and
+//   dL/dalpha_j = dL/dw_j * T_j - S_j / (1 - alpha_j + 1e-10).
+__global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__ off, int n_rays,
+                                                         const float* __restrict__ sigfeat,
+                                                         const float* __restrict__ dist,
+                                                         const float* __restrict__ weight,
+                                                         const float* __restrict__ trans,
+                                                         const int* __restrict__ app_of,
+                                                         const float* __restrict__ rgb,
+                                                         const float* __restrict__ rgb_pre,
+                                                         const float* __restrict__ g_rgb,
+                                                         const float* __restrict__ g_acc, float shift, int act,
+                                                         float dscale, int white_bg, int shade_act,
+                                                         float* __restrict__ dout, float* __restrict__ dsig,
+                                                         float* __restrict__ dnorm) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rays; r += nwarps) {
+        const int b = off[r], e = off[r + 1];
+        float gm[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float pre = rgb_pre[3 * r + c];
+            gm[c] = (pre >= 0.0f && pre <= 1.0f) ? g_rgb[3 * r + c] : 0.0f;      // clamp backward
+        }
+        const float dacc = (g_acc ? g_acc[r] : 0.0f) - (white_bg ? (gm[0] + gm[1] + gm[2]) : 0.0f);
+        float carry = 0.f, dn = 0.f;
+        const int len = e - b;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;                 // reverse index: j = e-1-i
+            const int j = e - 1 - i;
+            float dw = 0.f, w = 0.f;
+            if (i < len) {
+                w = weight[j];
+                dw = dacc;
+                const int a = app_of[j];
+                if (a >= 0) {
+                    const float r0 = rgb[4 * (size_t)a + 0], r1 = rgb[4 * (size_t)a + 1], r2 = rgb[4 * (size_t)a + 2];
+                    dw += gm[0] * r0 + gm[1] * r1 + gm[2] * r2;
+                    float d0 = w * gm[0], d1 = w * gm[1], d2 = w * gm[2];
+                    if (shade_act == 1) { d0 *= r0 * (1.f - r0); d1 *= r1 * (1.f - r1); d2 *= r2 * (1.f - r2); }
+                    else if (shade_act == 2) { d0 = r0 > 0.f ? d0 : 0.f; d1 = r1 > 0.f ? d1 : 0.f; d2 = r2 > 0.f ? d2 : 0.f; }
+                    *reinterpret_cast<float4*>(dout + 4 * (size_t)a) = make_float4(d0, d1, d2, 0.f);
+                }
+            }
+            float s = dw * w;                        // inclusive scan in reverse order
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float v = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += v;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, s, 1);
+            if (lane == 0) excl = 0.f;
+            const float suffix = carry + excl;       // sum over samples behind j
+            if (i < len) {
+                const float x = sigfeat[j] + shift;
+                const float sigma = density_act(x, act);
+                const float dd = dist[j] * dscale;
+                const float ex = expf(-sigma * dd);
+                const float alpha = 1.0f - ex;
+                const float q = 1.0f - alpha + 1e-10f;
+                const float dalpha = dw * trans[j] - suffix / q;
+                const float dsigma = dalpha * dd * ex;
+                dsig[j] = dsigma * density_act_grad(x, act);
+                dn += dalpha * sigma * ex * dd;      // d/d(norm) * norm
+            }
+            carry += __shfl_sync(0xffffffffu, s, 31);
+        }
+        if (dnorm) {
+            dn = warp_sum(dn);
+            if (lane == 0) dnorm[r] = dn;
+        }
+    }
+}
+
+// per ray: dL/d rays_o = sum_j dL/du_j * inv;  dL/d rays_d = sum_j dL/du_j * inv * t_j
+// (+ NDC: dists = dz*|d|  ->  dL/d d += dnorm_r/|d| * d/|d|).
+__global__ void __launch_bounds__(256) ray_bwd_kernel(const int* __restrict__ off, int n_rays,
+                                                      const float4* __restrict__ samp,
+                                                      const float4* __restrict__ dsamp,
+                                                      const float* __restrict__ rays_d,
+                                                      const float* __restrict__ dnorm, float i0, float i1, float i2,
+                                                      float* __restrict__ d_o, float* __restrict__ d_d) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < n_rays; r += nwarps) {
+        const int b = off[r], e = off[r + 1];
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        for (int j = b + lane; j < e; j += 32) {
+            const float4 g = dsamp[j];
+            const float t = samp[j].w;
+            const float gx = g.x * i0, gy = g.y * i1, gz = g.z * i2;
+            o0 += gx; o1 += gy; o2 += gz;
+            d0 += gx * t; d1 += gy * t; d2 += gz * t;
+        }
+        o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2);
+        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+        if (lane == 0) {
+            if (dnorm) {
+                const float x = rays_d[3 * r], y = rays_d[3 * r + 1], z = rays_d[3 * r + 2];
+                const float n2 = x * x + y * y + z * z;
+                const float k = n2 > 0.f ? dnorm[r] / n2 : 0.f;    // dnorm holds dL/dnorm * norm
+                d0 += k * x; d1 += k * y; d2 += k * z;
+            }
+            d_o[3 * r] = o0; d_o[3 * r + 1] = o1; d_o[3 * r + 2] = o2;
+            d_d[3 * r] = d0; d_d[3 * r + 1] = d1; d_d[3 * r + 2] = d2;
+        }
+    }
+}
+
+static int ray_grid(int n_rays) {
+    int want = (n_rays + 7) / 8;
+    int cap = kNumSMs * 8;
+    return want < cap ? (want < 1 ? 1 : want) : cap;
+}
+
+}  // namespace jt
+
+using namespace jt;
+
+extern "C" int jt_alpha_fwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist,
+                            const float* samp, float density_shift, int act, float distance_scale, float thres,
+                            float* weight, float* trans, float* acc, float* wz, int* app_cnt, int* app_off,
+                            int* aidx, int* app_of, cudaStream_t stream) {
+    JT_CHECK_ARG(ray_off && sigfeat && dist && samp && weight && trans && acc && wz && app_cnt && app_off && aidx && app_of);
+    JT_CHECK_ARG(act == 0 || act == 1);
+    if (n_rays <= 0) return JT_OK;
+    int grid = ray_grid(n_rays);
+    g_launches += 2;
+    alpha_fwd_kernel<<<grid, 256, 0, stream>>>(ray_off, n_rays, sigfeat, dist, reinterpret_cast<const float4*>(samp),
+                                               density_shift, act, distance_scale, thres, weight, trans, acc, wz,
+                                               app_cnt);
+    if (int rc = jt_exclusive_scan(app_cnt, app_off, n_rays, stream)) return rc;
+    app_fill_kernel<<<grid, 256, 0, stream>>>(ray_off, app_off, n_rays, weight, thres, aidx, app_of);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_composite_fwd(const int* app_off, int n_rays, const int* aidx, const float* weight,
+                                const float* rgb, const float* acc, const float* wz, const float* rays_d,
+                                int white_bg, float depth_bias, float* rgb_pre, float* rgb_map, float* depth,
+                                float* opacity, cudaStream_t stream) {
+    JT_CHECK_ARG(app_off && aidx && weight && rgb && acc && wz && rays_d && rgb_pre && rgb_map && depth && opacity);
+    if (n_rays <= 0) return JT_OK;
+    g_launches += 1;
+    composite_fwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(app_off, n_rays, aidx, weight, rgb, acc, wz, rays_d,
+                                                               white_bg, depth_bias, rgb_pre, rgb_map, depth, opacity);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_render_bwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist,
+                             const float* weight, const float* trans, const int* app_of, const float* rgb,
+                             const float* rgb_pre, const float* g_rgb, const float* g_acc, float density_shift,
+                             int act, float distance_scale, int white_bg, int shade_act, float* dout, float* dsig,
+                             float* dnorm, cudaStream_t stream) {
+    JT_CHECK_ARG(ray_off && sigfeat && dist && weight && trans && app_of && rgb && rgb_pre && g_rgb && dout && dsig);
+    if (n_rays <= 0) return JT_OK;
+    g_launches += 1;
+    render_bwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(ray_off, n_rays, sigfeat, dist, weight, trans, app_of, rgb,
+                                                            rgb_pre, g_rgb, g_acc, density_shift, act, distance_scale,
+                                                            white_bg, shade_act, dout, dsig, dnorm);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* dsamp,
+                          const float* rays_d, const float* dnorm, const float* h_inv, float* d_o, float* d_d,
+                          cudaStream_t stream) {
+    JT_CHECK_ARG(ray_off && samp && dsamp && rays_d && h_inv && d_o && d_d);
+    if (n_rays <= 0) return JT_OK;
+    g_launches += 1;
+    ray_bwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(ray_off, n_rays, reinterpret_cast<const float4*>(samp),
+                                                         reinterpret_cast<const float4*>(dsamp), rays_d, dnorm,
+                                                         h_inv[0], h_inv[1], h_inv[2], d_o, d_d);
+    JT_RETURN_LAUNCH();
+}

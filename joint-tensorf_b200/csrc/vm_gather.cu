@@ -1,0 +1,229 @@
+// K2 -- plane x line VM feature interpolation, forward and backward.
+//
+// Replaces reference BAT_VMSplit.compute_densityfeature (bateRF.py:41-94; twin
+// tensoRF.py:230-251) and the gather part of compute_appfeature
+// (bateRF.py:97-128; twin tensoRF.py:254-268), i.e. the 12 F.grid_sample calls
+// per forward and their grid_sampler_2d_backward atomics.
+//
+// Layout: factors are channel-last ([H][W][C] planes, [L][C] lines) so one
+// bilinear tap of all channels is one contiguous vector. Four lanes share a
+// sample; lane `sub` owns channel quads sub, sub+4, ... and loads them as
+// float4 (16 B), so the four lanes of a sample read 64 contiguous bytes per
+// tap and a warp covers 8 consecutive samples of (mostly) one ray, whose taps
+// overlap in L1. The backward pass re-reads the taps (for the coordinate
+// gradient that drives the pose optimisation, bateRF.py:44-46 does not detach
+// coordinates) and scatters factor gradients with 16-byte vector RED
+// operations.
+#include "jt_common.cuh"
+#include "../../include/jt_vm.h"
+
+namespace jt {
+
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 f4_lerp2(float4 a, float wa, float4 b, float wb) {
+    return make_float4(a.x * wa + b.x * wb, a.y * wa + b.y * wb, a.z * wa + b.z * wb, a.w * wa + b.w * wb);
+}
+__device__ __forceinline__ float4 f4_bilin(float4 a, float wa, float4 b, float wb, float4 c, float wc, float4 d, float wd) {
+    return make_float4(a.x * wa + b.x * wb + c.x * wc + d.x * wd, a.y * wa + b.y * wb + c.y * wc + d.y * wd,
+                       a.z * wa + b.z * wb + c.z * wc + d.z * wd, a.w * wa + b.w * wb + c.w * wc + d.w * wd);
+}
+
+struct PlaneTaps {
+    const float *p00, *p10, *p01, *p11, *l0, *l1;
+    size_t o00, o10, o01, o11, ol0, ol1;     // element offsets (shared by value and gradient buffers)
+    float w00, w10, w01, w11;
+    Tap tx, ty, tl;
+};
+
+__device__ __forceinline__ PlaneTaps plane_taps(const Factors& F, int i, const float u[3]) {
+    PlaneTaps t;
+    t.tx = make_tap(u[mat0(i)], F.W[i]);
+    t.ty = make_tap(u[mat1(i)], F.H[i]);
+    t.tl = make_tap(u[vecm(i)], F.L[i]);
+    const size_t C = F.C[i];
+    size_t r0 = (size_t)t.ty.i0 * F.W[i], r1 = (size_t)t.ty.i1 * F.W[i];
+    t.o00 = (r0 + t.tx.i0) * C; t.o10 = (r0 + t.tx.i1) * C;
+    t.o01 = (r1 + t.tx.i0) * C; t.o11 = (r1 + t.tx.i1) * C;
+    t.ol0 = (size_t)t.tl.i0 * C; t.ol1 = (size_t)t.tl.i1 * C;
+    t.p00 = F.plane[i] + t.o00; t.p10 = F.plane[i] + t.o10;
+    t.p01 = F.plane[i] + t.o01; t.p11 = F.plane[i] + t.o11;
+    t.l0 = F.line[i] + t.ol0; t.l1 = F.line[i] + t.ol1;
+    t.w00 = t.tx.w0 * t.ty.w0; t.w10 = t.tx.w1 * t.ty.w0;     // nw, ne
+    t.w01 = t.tx.w0 * t.ty.w1; t.w11 = t.tx.w1 * t.ty.w1;     // sw, se
+    return t;
+}
+
+// APP == false: out[e] = sum_i sum_c P_ic * L_ic               (density feature)
+// APP == true : out[e][off_i + c] = P_ic * L_ic                (appearance components, before basis_mat)
+template <bool APP>
+__global__ void __launch_bounds__(256) vm_fwd_kernel(Factors F, const float4* __restrict__ samp,
+                                                     const int* __restrict__ slot, const int* __restrict__ n_dev,
+                                                     int n_fixed, float* __restrict__ out) {
+    const int n = n_dev ? *n_dev : n_fixed;
+    const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 8; base < n; base += nwarps * 8) {
+        const int e = base + grp;
+        const bool act = e < n;
+        float acc = 0.f;
+        if (act) {
+            const int j = slot ? slot[e] : e;
+            const float4 u4 = samp[j];
+            const float u[3] = {u4.x, u4.y, u4.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const PlaneTaps t = plane_taps(F, i, u);
+                const int C = F.C[i];
+                for (int q = sub * 4; q < C; q += 16) {
+                    float4 a = ldg4(t.p00 + q), b = ldg4(t.p10 + q), c = ldg4(t.p01 + q), d = ldg4(t.p11 + q);
+                    float4 la = ldg4(t.l0 + q), lb = ldg4(t.l1 + q);
+                    float4 pv = f4_bilin(a, t.w00, b, t.w10, c, t.w01, d, t.w11);
+                    float4 lv = f4_lerp2(la, t.tl.w0, lb, t.tl.w1);
+                    if (APP) {
+                        *reinterpret_cast<float4*>(out + (size_t)e * F.ctot + F.off[i] + q) = f4_mul(pv, lv);
+                    } else {
+                        acc += f4_dot(pv, lv);
+                    }
+                }
+            }
+        }
+        if (!APP) {
+            acc = quad_sum(acc);
+            if (act && sub == 0) out[e] = acc;
+        }
+    }
+}
+
+// Backward of the above. gin: density -> dL/dsigma_feature [n]; app -> dL/dcomponents [n][ctot].
+// dsamp[j] (float4, xyz used) receives dL/du in normalised coordinates; `accumulate`
+// selects store (density pass, runs first) or add (appearance pass; each sample
+// slot appears at most once in `slot`, so the read-modify-write has one owner).
+template <bool APP>
+__global__ void __launch_bounds__(256) vm_bwd_kernel(Factors F, FactorGrads G, const float4* __restrict__ samp,
+                                                     const int* __restrict__ slot, const int* __restrict__ n_dev,
+                                                     int n_fixed, const float* __restrict__ gin,
+                                                     float4* __restrict__ dsamp, int accumulate) {
+    const int n = n_dev ? *n_dev : n_fixed;
+    const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int base = warp * 8; base < n; base += nwarps * 8) {
+        const int e = base + grp;
+        const bool act = e < n;
+        float du[3] = {0.f, 0.f, 0.f};
+        int j = 0;
+        if (act) {
+            j = slot ? slot[e] : e;
+            const float4 u4 = samp[j];
+            const float u[3] = {u4.x, u4.y, u4.z};
+            const float gs = APP ? 0.f : gin[e];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const PlaneTaps t = plane_taps(F, i, u);
+                const int C = F.C[i];
+                float sx = 0.f, sy = 0.f, sl = 0.f;
+                for (int q = sub * 4; q < C; q += 16) {
+                    float4 a = ldg4(t.p00 + q), b = ldg4(t.p10 + q), c = ldg4(t.p01 + q), d = ldg4(t.p11 + q);
+                    float4 la = ldg4(t.l0 + q), lb = ldg4(t.l1 + q);
+                    float4 g4 = APP ? ldg4(gin + (size_t)e * F.ctot + F.off[i] + q) : make_float4(gs, gs, gs, gs);
+                    float4 pv = f4_bilin(a, t.w00, b, t.w10, c, t.w01, d, t.w11);
+                    float4 lv = f4_lerp2(la, t.tl.w0, lb, t.tl.w1);
+                    float4 gl = f4_mul(g4, lv);      // dL/dP (interpolated)
+                    float4 gp = f4_mul(g4, pv);      // dL/dL (interpolated)
+                    if (t.w00 != 0.f) red_add_v4(G.plane[i] + t.o00 + q, f4_scale(gl, t.w00));
+                    if (t.w10 != 0.f) red_add_v4(G.plane[i] + t.o10 + q, f4_scale(gl, t.w10));
+                    if (t.w01 != 0.f) red_add_v4(G.plane[i] + t.o01 + q, f4_scale(gl, t.w01));
+                    if (t.w11 != 0.f) red_add_v4(G.plane[i] + t.o11 + q, f4_scale(gl, t.w11));
+                    if (t.tl.w0 != 0.f) red_add_v4(G.line[i] + t.ol0 + q, f4_scale(gp, t.tl.w0));
+                    if (t.tl.w1 != 0.f) red_add_v4(G.line[i] + t.ol1 + q, f4_scale(gp, t.tl.w1));
+                    // d/d index (ATen grid_sampler_2d_backward: out-of-range taps read as 0)
+                    float4 dpx = f4_lerp2(f4_lerp2(b, t.tx.m1, a, -t.tx.m0), t.ty.w0,
+                                          f4_lerp2(d, t.tx.m1, c, -t.tx.m0), t.ty.w1);
+                    float4 dpy = f4_lerp2(f4_lerp2(c, t.ty.m1, a, -t.ty.m0), t.tx.w0,
+                                          f4_lerp2(d, t.ty.m1, b, -t.ty.m0), t.tx.w1);
+                    float4 dl = f4_lerp2(lb, t.tl.m1, la, -t.tl.m0);
+                    sx += f4_dot(gl, dpx);
+                    sy += f4_dot(gl, dpy);
+                    sl += f4_dot(gp, dl);
+                }
+                du[mat0(i)] += sx * t.tx.scale;
+                du[mat1(i)] += sy * t.ty.scale;
+                du[vecm(i)] += sl * t.tl.scale;
+            }
+        }
+        du[0] = quad_sum(du[0]); du[1] = quad_sum(du[1]); du[2] = quad_sum(du[2]);
+        if (act && sub == 0 && dsamp) {
+            float4 v = make_float4(du[0], du[1], du[2], 0.f);
+            if (accumulate) { float4 o = dsamp[j]; v.x += o.x; v.y += o.y; v.z += o.z; }
+            dsamp[j] = v;
+        }
+    }
+}
+
+static int fill_factors(Factors& F, const void* const* ptrs, const int* dims) {
+    int off = 0;
+    for (int i = 0; i < 3; ++i) {
+        F.plane[i] = static_cast<const float*>(ptrs[i]);
+        F.line[i] = static_cast<const float*>(ptrs[3 + i]);
+        F.H[i] = dims[i]; F.W[i] = dims[3 + i]; F.L[i] = dims[6 + i]; F.C[i] = dims[9 + i];
+        if (!F.plane[i] || !F.line[i]) return JT_ERR_ARG;
+        if (F.C[i] <= 0 || (F.C[i] & 3) || F.H[i] < 1 || F.W[i] < 1 || F.L[i] < 1) return JT_ERR_ARG;
+        F.off[i] = off;
+        off += F.C[i];
+    }
+    F.ctot = off;
+    return JT_OK;
+}
+
+static int grid_for(int n_hint) {
+    long long want = ((long long)n_hint + 63) / 64;            // 64 samples per CTA pass
+    long long cap = (long long)kNumSMs * 8;
+    long long g = want < cap ? want : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace jt
+
+using namespace jt;
+
+extern "C" int jt_vm_gather_fwd(int app, const void* const* h_factors, const int* h_dims, const float* samp,
+                                const int* slot, const int* n_dev, int n_max, float* out, cudaStream_t stream) {
+    JT_CHECK_ARG(h_factors && h_dims && samp && out);
+    if (n_max <= 0) return JT_OK;
+    Factors F;
+    if (int rc = fill_factors(F, h_factors, h_dims)) return rc;
+    int grid = grid_for(n_max);
+    g_launches += 1;
+    if (app)
+        vm_fwd_kernel<true><<<grid, 256, 0, stream>>>(F, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max, out);
+    else
+        vm_fwd_kernel<false><<<grid, 256, 0, stream>>>(F, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max, out);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_factor_grads,
+                                const int* h_dims, const float* samp, const int* slot, const int* n_dev,
+                                int n_max, const float* gin, float* dsamp, int accumulate, cudaStream_t stream) {
+    JT_CHECK_ARG(h_factors && h_factor_grads && h_dims && samp && gin);
+    if (n_max <= 0) return JT_OK;
+    Factors F;
+    if (int rc = fill_factors(F, h_factors, h_dims)) return rc;
+    FactorGrads G;
+    for (int i = 0; i < 3; ++i) {
+        G.plane[i] = static_cast<float*>(h_factor_grads[i]);
+        G.line[i] = static_cast<float*>(h_factor_grads[3 + i]);
+        JT_CHECK_ARG(G.plane[i] && G.line[i]);
+    }
+    int grid = grid_for(n_max);
+    g_launches += 1;
+    if (app)
+        vm_bwd_kernel<true><<<grid, 256, 0, stream>>>(F, G, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max,
+                                                      gin, reinterpret_cast<float4*>(dsamp), accumulate);
+    else
+        vm_bwd_kernel<false><<<grid, 256, 0, stream>>>(F, G, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max,
+                                                       gin, reinterpret_cast<float4*>(dsamp), accumulate);
+    JT_RETURN_LAUNCH();
+}

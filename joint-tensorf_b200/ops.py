@@ -1,0 +1,317 @@
+"""Torch-tensor wrappers over the C ABI (include/jt_vm.h) + the autograd glue.
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream, and its
+autograd engine calls our backward kernels. All arithmetic of the hot path is in
+csrc/*.cu. Nothing in this file computes on the CPU or falls back to ATen
+operators for the hot path.
+"""
+import contextlib
+
+import torch
+
+from . import _lib
+from ._lib import check, floats, ints, ptrs
+
+MAT_MODE = ((0, 1), (0, 2), (1, 2))   # reference tensorBase.py:405
+VEC_MODE = (2, 1, 0)                  # reference tensorBase.py:406
+
+
+# ------------------------------------------------------------------ per-kernel timing (bench.py)
+class KernelTimer:
+    """Optional CUDA-event timing around each C-ABI call (enabled by bench.py for the
+    roofline breakdown; off in normal runs so the hot path records no events)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []      # (name, start_event, end_event)
+
+    @contextlib.contextmanager
+    def span(self, name):
+        if not self.enabled:
+            yield
+            return
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.append((name, s, e))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            tot, cnt = out.get(name, (0.0, 0))
+            out[name] = (tot + s.elapsed_time(e), cnt + 1)
+        self.records = []
+        return out
+
+
+TIMER = KernelTimer()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.JtError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+
+
+# ------------------------------------------------------------------ factors
+def phys_cl(x):
+    """[1,C,H,W] tensor -> its channel-last physical view [H,W,C] (contiguous fp32)."""
+    assert x.dim() == 4 and x.shape[0] == 1, x.shape
+    xp = x.permute(0, 2, 3, 1)
+    if not xp.is_contiguous():
+        xp = xp.contiguous()
+    if xp.dtype != torch.float32:
+        xp = xp.float()
+    return xp[0]
+
+
+class FactorSet:
+    """Three planes + three lines in channel-last physical form and their dims."""
+
+    def __init__(self, planes, lines):
+        self.planes = [phys_cl(p) for p in planes]            # [H,W,C]
+        self.lines = [phys_cl(l)[:, 0, :] for l in lines]     # [L,C]
+        self.C = [p.shape[2] for p in self.planes]
+        for i in range(3):
+            if self.C[i] % 4 != 0 or self.lines[i].shape[1] != self.C[i]:
+                raise _lib.JtError(f"component count {self.C[i]} must be a multiple of 4 and match its line")
+        self.dims = ints([p.shape[0] for p in self.planes] + [p.shape[1] for p in self.planes] +
+                         [l.shape[0] for l in self.lines] + self.C)
+        self.ptrs = ptrs([p.data_ptr() for p in self.planes] + [l.data_ptr() for l in self.lines])
+        self.ctot = sum(self.C)
+
+    def zero_grads(self):
+        gp = [torch.zeros_like(p) for p in self.planes]
+        gl = [torch.zeros_like(l) for l in self.lines]
+        return gp, gl
+
+    @staticmethod
+    def grads_as_nchw(gp, gl):
+        """physical [H,W,C] / [L,C] gradients -> logical [1,C,H,W] / [1,C,L,1] views."""
+        return ([g.unsqueeze(0).permute(0, 3, 1, 2) for g in gp],
+                [g.unsqueeze(0).unsqueeze(2).permute(0, 3, 1, 2) for g in gl])
+
+
+# ------------------------------------------------------------------ K1
+def sample_ray_dense(rays_o, rays_d, aux, ndc, n_samples, geom, mask=None):
+    _need_cuda(rays_o, "rays_o")
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    pts = torch.empty((n, n_samples, 3), device=dev)
+    z = torch.empty((n, n_samples), device=dev)
+    valid = torch.empty((n, n_samples), device=dev, dtype=torch.uint8)
+    mb, md, mg = (mask.bits, mask.h_dims, mask.h_geom) if mask is not None else (None, None, None)
+    with TIMER.span("sample_ray_dense"):
+        check(_lib.lib().jt_sample_ray_dense(_p(rays_o), _p(rays_d), _p(aux), int(ndc), n, n_samples, geom,
+                                             _p(mb), md, mg, _p(pts), _p(z), _p(valid), _stream()),
+              "jt_sample_ray_dense")
+    return pts, z, valid.bool()
+
+
+class Compacted:
+    """Result of jt_march_compact (all device tensors, capacity N*S)."""
+    __slots__ = ("n_rays", "n_samples", "cap", "ray_off", "sidx", "samp", "dist", "count")
+
+
+def march_compact(rays_o, rays_d, aux, ndc, n_samples, geom, mask=None):
+    _need_cuda(rays_o, "rays_o")
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    cap = max(n * n_samples, 1)
+    c = Compacted()
+    c.n_rays, c.n_samples, c.cap = n, n_samples, cap
+    ray_cnt = torch.empty((max(n, 1),), device=dev, dtype=torch.int32)
+    c.ray_off = torch.zeros((n + 1,), device=dev, dtype=torch.int32)
+    c.sidx = torch.empty((cap,), device=dev, dtype=torch.int32)
+    c.samp = torch.empty((cap, 4), device=dev)
+    c.dist = torch.empty((cap,), device=dev)
+    mb, md, mg = (mask.bits, mask.h_dims, mask.h_geom) if mask is not None else (None, None, None)
+    with TIMER.span("march_compact"):
+        check(_lib.lib().jt_march_compact(_p(rays_o), _p(rays_d), _p(aux), int(ndc), n, n_samples, geom,
+                                          _p(mb), md, mg, _p(ray_cnt), _p(c.ray_off), _p(c.sidx), _p(c.samp),
+                                          _p(c.dist), _stream()), "jt_march_compact")
+    c.count = c.ray_off[n:n + 1]          # device scalar V (never read on the host in the hot path)
+    return c
+
+
+# ------------------------------------------------------------------ K2
+def vm_gather_fwd(app, fs, samp, slot, n_dev, n_max, out):
+    with TIMER.span("vm_app_fwd" if app else "vm_density_fwd"):
+        check(_lib.lib().jt_vm_gather_fwd(int(app), fs.ptrs, fs.dims, _p(samp), _p(slot), _p(n_dev), int(n_max),
+                                          _p(out), _stream()), "jt_vm_gather_fwd")
+
+
+def vm_gather_bwd(app, fs, gp, gl, samp, slot, n_dev, n_max, gin, dsamp, accumulate):
+    gptrs = ptrs([g.data_ptr() for g in gp] + [g.data_ptr() for g in gl])
+    with TIMER.span("vm_app_bwd" if app else "vm_density_bwd"):
+        check(_lib.lib().jt_vm_gather_bwd(int(app), fs.ptrs, gptrs, fs.dims, _p(samp), _p(slot), _p(n_dev),
+                                          int(n_max), _p(gin), _p(dsamp), int(accumulate), _stream()),
+              "jt_vm_gather_bwd")
+
+
+# ------------------------------------------------------------------ K3
+def gemm_nt(x, ldx, w, ldw, w_kn, bias, y, ldy, mask, ldm, m_dev, m_max, n, k, act, name="gemm_nt",
+            x_off=0, w_off=0, y_off=0, mask_off=0):
+    """offsets are in floats (used to address column blocks of a wider buffer)."""
+    with TIMER.span(name):
+        check(_lib.lib().jt_gemm_nt(_p(x) + 4 * x_off, ldx, _p(w) + 4 * w_off, ldw, int(w_kn), _p(bias),
+                                    _p(y) + 4 * y_off, ldy, (_p(mask) + 4 * mask_off) if mask is not None else 0,
+                                    ldm, _p(m_dev), int(m_max), n, k, act, _stream()), "jt_gemm_nt")
+
+
+def gemm_tn(dy, ldy, x, ldx, m_dev, m_max, n, k, dw, ldw, db, name="gemm_tn", dy_off=0, x_off=0, dw_off=0):
+    with TIMER.span(name):
+        check(_lib.lib().jt_gemm_tn(_p(dy) + 4 * dy_off, ldy, _p(x) + 4 * x_off, ldx, _p(m_dev), int(m_max), n, k,
+                                    _p(dw) + 4 * dw_off, ldw, _p(db), _stream()), "jt_gemm_tn")
+
+
+def pe_encode(bwd, app_dim, fea_pe, view_pe, mode, fprog, vprog, n_samples, normalize_dir, feat, ldf, aidx, sidx,
+              rays_d, n_dev, n_max, out, ldo, out2=None, ldo2=0, din=None, ldi=0):
+    with TIMER.span("pe_bwd" if bwd else "pe_fwd"):
+        check(_lib.lib().jt_pe_encode(int(bwd), app_dim, fea_pe, view_pe, mode, float(fprog), float(vprog),
+                                      n_samples, int(normalize_dir), _p(feat), ldf, _p(aidx), _p(sidx), _p(rays_d),
+                                      _p(n_dev), int(n_max), _p(out), ldo, _p(out2), ldo2, _p(din), ldi, _stream()),
+              "jt_pe_encode")
+
+
+def sh_shade(bwd, feat, ldf, aidx, sidx, rays_d, n_samples, normalize_dir, n_dev, n_max, rgb, dout, dfeat, ldd):
+    with TIMER.span("sh_bwd" if bwd else "sh_fwd"):
+        check(_lib.lib().jt_sh_shade(int(bwd), _p(feat), ldf, _p(aidx), _p(sidx), _p(rays_d), n_samples,
+                                     int(normalize_dir), _p(n_dev), int(n_max), _p(rgb), _p(dout), _p(dfeat), ldd,
+                                     _stream()), "jt_sh_shade")
+
+
+# ------------------------------------------------------------------ K5
+def blur_cl(x_phys, h, w, c, taps, axes, adjoint):
+    """x_phys: contiguous fp32 buffer holding h*w*c floats, interpreted as [h][w][c]."""
+    out = torch.empty_like(x_phys)
+    tmp = torch.empty_like(x_phys) if axes == 3 else None
+    with TIMER.span("blur_adj" if adjoint else "blur_fwd"):
+        check(_lib.lib().jt_blur_cl(_p(x_phys), _p(out), _p(tmp), h, w, c, _p(taps), taps.numel(), axes,
+                                    int(adjoint), _stream()), "jt_blur_cl")
+    return out
+
+
+class BlurFactor(torch.autograd.Function):
+    """Separable blur of one VM factor ([1,C,H,W] logical shape, channel-last memory).
+
+    `hq, wq` are the (H', W') the reference passes to convolute_plane
+    (bateRF.py:68,76,117): (g[m0], g[m1]) although storage is [g[m1], g[m0]] -- a
+    re-interpretation of the buffer on non-cubic grids.
+    In channel-last memory the re-interpretation is the same statement: treat the
+    [H][W][C] buffer as [H'][W'][C]. Output logical shape: [1,C,H',W']."""
+
+    @staticmethod
+    def forward(ctx, x, taps, hq, wq, axes):
+        _need_cuda(x, "factor")
+        xp = phys_cl(x)
+        c = xp.shape[2]
+        assert xp.shape[0] * xp.shape[1] == hq * wq
+        y = blur_cl(xp, hq, wq, c, taps, axes, 0)
+        ctx.save_for_backward(taps)
+        ctx.meta = (tuple(xp.shape), hq, wq, c, axes)
+        return y.view(1, hq, wq, c).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (taps,) = ctx.saved_tensors
+        shape, hq, wq, c, axes = ctx.meta
+        gp = phys_cl(gy)
+        gx = blur_cl(gp, hq, wq, c, taps, axes, 1)
+        return gx.view(1, *shape).permute(0, 3, 1, 2), None, None, None, None
+
+
+# ------------------------------------------------------------------ standalone feature ops (API parity)
+def _samp_from_xyz(xyz_norm):
+    n = xyz_norm.shape[0]
+    samp = torch.zeros((max(n, 1), 4), device=xyz_norm.device)
+    samp[:n, :3] = xyz_norm.detach()
+    return samp
+
+
+class DensityFeature(torch.autograd.Function):
+    """compute_densityfeature(xyz_norm) as a differentiable op (bateRF.py:41-94)."""
+
+    @staticmethod
+    def forward(ctx, xyz, *factors):
+        _need_cuda(xyz, "xyz_sampled")
+        fs = FactorSet(factors[:3], factors[3:])
+        n = xyz.shape[0]
+        samp = _samp_from_xyz(xyz)
+        out = torch.empty((max(n, 1),), device=xyz.device)
+        vm_gather_fwd(0, fs, samp, None, None, n, out)
+        ctx.fs, ctx.samp, ctx.n = fs, samp, n
+        return out[:n]
+
+    @staticmethod
+    def backward(ctx, g):
+        fs, samp, n = ctx.fs, ctx.samp, ctx.n
+        gp, gl = fs.zero_grads()
+        dsamp = torch.zeros_like(samp)
+        vm_gather_bwd(0, fs, gp, gl, samp, None, None, n, g.contiguous().float(), dsamp, 0)
+        gpn, gln = FactorSet.grads_as_nchw(gp, gl)
+        return (dsamp[:n, :3], *gpn, *gln)
+
+
+class AppComponents(torch.autograd.Function):
+    """plane*line products [A, sum C_app] feeding basis_mat (bateRF.py:97-128)."""
+
+    @staticmethod
+    def forward(ctx, xyz, *factors):
+        _need_cuda(xyz, "xyz_sampled")
+        fs = FactorSet(factors[:3], factors[3:])
+        n = xyz.shape[0]
+        samp = _samp_from_xyz(xyz)
+        out = torch.empty((max(n, 1), fs.ctot), device=xyz.device)
+        vm_gather_fwd(1, fs, samp, None, None, n, out)
+        ctx.fs, ctx.samp, ctx.n = fs, samp, n
+        return out[:n]
+
+    @staticmethod
+    def backward(ctx, g):
+        fs, samp, n = ctx.fs, ctx.samp, ctx.n
+        gp, gl = fs.zero_grads()
+        dsamp = torch.zeros_like(samp)
+        vm_gather_bwd(1, fs, gp, gl, samp, None, None, n, g.contiguous().float(), dsamp, 0)
+        gpn, gln = FactorSet.grads_as_nchw(gp, gl)
+        return (dsamp[:n, :3], *gpn, *gln)
+
+
+class Linear(torch.autograd.Function):
+    """y = x W^T (+ b) through jt_gemm_nt / jt_gemm_tn (used by compute_appfeature's basis_mat)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        m, k = x.shape
+        n = w.shape[0]
+        ldx, ldy = (k + 3) & ~3, (n + 3) & ~3
+        xp = x if (ldx == k and x.is_contiguous()) else torch.nn.functional.pad(x, (0, ldx - k)).contiguous()
+        y = torch.empty((max(m, 1), ldy), device=x.device)
+        wc = w.contiguous()
+        gemm_nt(xp, ldx, wc, k, 0, b, y, ldy, None, 0, None, m, n, k, 0, name="basis_fwd")
+        ctx.save_for_backward(xp, wc)
+        ctx.meta = (m, n, k, ldx, ldy, b is not None)
+        return y[:m, :n]
+
+    @staticmethod
+    def backward(ctx, gy):
+        xp, wc = ctx.saved_tensors
+        m, n, k, ldx, ldy, has_b = ctx.meta
+        g = torch.zeros((max(m, 1), ldy), device=gy.device)
+        g[:m, :n] = gy
+        gx = torch.empty((max(m, 1), ldx), device=gy.device)
+        gemm_nt(g, ldy, wc, k, 1, None, gx, ldx, None, 0, None, m, k, n, 0, name="basis_bwd_x")
+        gw = torch.zeros_like(wc)
+        gb = torch.zeros((n,), device=gy.device) if has_b else None
+        gemm_tn(g, ldy, xp, ldx, None, m, n, k, gw, k, gb, name="basis_bwd_w")
+        return gx[:m, :k], gw, gb

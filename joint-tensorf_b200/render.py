@@ -1,0 +1,259 @@
+"""The fused render op: one autograd node for the whole L1 forward/backward.
+
+Sequence of C-ABI calls for one batch of rays (all on the current stream, no
+host synchronisation anywhere -- the reference syncs at every boolean-mask
+index):
+
+  forward   jt_march_compact -> jt_vm_gather_fwd(density) -> jt_alpha_fwd
+            -> jt_vm_gather_fwd(app) -> jt_gemm_nt(basis) -> shading head
+            -> jt_composite_fwd
+  backward  jt_render_bwd -> jt_vm_gather_bwd(density) -> head backward
+            -> jt_vm_gather_bwd(app) -> jt_ray_bwd
+
+Sample counts (V valid samples, A appearance samples) stay on the device; the
+kernels read them from `ray_off[N]` / `app_off[N]` and run persistent grids.
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import check, floats
+from .ops import FactorSet, TIMER, _p, _stream
+
+
+def _r4(n):
+    return (n + 3) & ~3
+
+
+class RenderCfg:
+    """Host-side description of one forward call (plain Python, no tensors)."""
+
+    def __init__(self, **kw):
+        self.n_samples = 0
+        self.ndc = False
+        self.white_bg = True
+        self.h_geom = None          # ctypes float[12]
+        self.h_inv = None           # ctypes float[3]
+        self.mask = None            # PackedMask or None
+        self.density_shift = -10.0
+        self.act = 0                # 0 softplus, 1 relu
+        self.distance_scale = 25.0
+        self.thres = 1e-4
+        self.depth_bias = 0.0       # -near + 0.05
+        self.shading = "MLP_Fea"
+        self.app_dim = 27
+        self.fea_pe = 2
+        self.view_pe = 2
+        self.hidden = 64
+        self.fea_prog = 1.0
+        self.view_prog = 1.0
+        self.__dict__.update(kw)
+
+
+class _Head:
+    """Forward/backward of the shading head on compacted appearance samples."""
+
+    @staticmethod
+    def forward(cfg, ws, feat, ldf, aidx, sidx, rays_d, a_count, cap, params, dev):
+        F, H = cfg.app_dim, cfg.hidden
+        rgb = torch.empty((cap, 4), device=dev)
+        if cfg.shading == "SH":
+            ops.sh_shade(0, feat, ldf, aidx, sidx, rays_d, cfg.n_samples, cfg.ndc, a_count, cap, rgb, None, None, 0)
+            return rgb
+        w1, b1, w2, b2, w3, b3 = params
+        if cfg.shading == "MLP_Fea":
+            in_dim = F + 3 + 2 * cfg.fea_pe * F + 6 * cfg.view_pe
+            ldi = _r4(in_dim)
+            x = torch.empty((cap, ldi), device=dev)
+            ops.pe_encode(0, F, cfg.fea_pe, cfg.view_pe, 0, cfg.fea_prog, cfg.view_prog, cfg.n_samples, cfg.ndc,
+                          feat, ldf, aidx, sidx, rays_d, a_count, cap, x, ldi)
+            h1 = torch.empty((cap, H), device=dev)
+            ops.gemm_nt(x, ldi, w1, in_dim, 0, b1, h1, H, None, 0, a_count, cap, H, in_dim, 1, name="mlp_l1_fwd")
+            h2 = torch.empty((cap, H), device=dev)
+            ops.gemm_nt(h1, H, w2, H, 0, b2, h2, H, None, 0, a_count, cap, H, H, 1, name="mlp_l2_fwd")
+            ops.gemm_nt(h2, H, w3, H, 0, b3, rgb, 4, None, 0, a_count, cap, 3, H, 2, name="mlp_l3_fwd")
+            ws.update(x=x, ldi=ldi, in_dim=in_dim, h1=h1, h2=h2)
+        elif cfg.shading == "MLP_Fea_WeakView":
+            in_dim = F + 2 * cfg.fea_pe * F
+            ldi = _r4(in_dim)
+            nv = 6 * cfg.view_pe
+            assert nv % 4 == 0, "view_pe must be even for the WeakView layout"
+            ldm = nv + H
+            x = torch.empty((cap, ldi), device=dev)
+            mid = torch.empty((cap, ldm), device=dev)
+            ops.pe_encode(0, F, cfg.fea_pe, cfg.view_pe, 1, cfg.fea_prog, cfg.view_prog, cfg.n_samples, cfg.ndc,
+                          feat, ldf, aidx, sidx, rays_d, a_count, cap, x, ldi, mid, ldm)
+            h1 = torch.empty((cap, H), device=dev)
+            ops.gemm_nt(x, ldi, w1, in_dim, 0, b1, h1, H, None, 0, a_count, cap, H, in_dim, 1, name="mlp_l1_fwd")
+            ops.gemm_nt(h1, H, w2, H, 0, b2, mid, ldm, None, 0, a_count, cap, H, H, 1, name="mlp_l2_fwd", y_off=nv)
+            ops.gemm_nt(mid, ldm, w3, ldm, 0, b3, rgb, 4, None, 0, a_count, cap, 3, ldm, 2, name="mlp_l3_fwd")
+            ws.update(x=x, ldi=ldi, in_dim=in_dim, h1=h1, mid=mid, ldm=ldm, nv=nv)
+        else:
+            raise _lib.JtError(f"shading model {cfg.shading!r} is not implemented by the B200 path")
+        return rgb
+
+    @staticmethod
+    def backward(cfg, ws, dout, feat, ldf, aidx, sidx, rays_d, a_count, cap, params, dev):
+        """dout [cap,4] -> dfeat [cap, ldf]; returns (dfeat, param grads list)."""
+        F, H = cfg.app_dim, cfg.hidden
+        dfeat = torch.empty((cap, ldf), device=dev)
+        if cfg.shading == "SH":
+            ops.sh_shade(1, feat, ldf, aidx, sidx, rays_d, cfg.n_samples, cfg.ndc, a_count, cap, None, dout, dfeat, ldf)
+            return dfeat, []
+        w1, b1, w2, b2, w3, b3 = params
+        gw1, gb1, gw2, gb2, gw3, gb3 = [torch.zeros_like(t) for t in params]
+        x, ldi, in_dim, h1 = ws["x"], ws["ldi"], ws["in_dim"], ws["h1"]
+        dh2 = torch.empty((cap, H), device=dev)
+        dh1 = torch.empty((cap, H), device=dev)
+        if cfg.shading == "MLP_Fea":
+            h2 = ws["h2"]
+            ops.gemm_tn(dout, 4, h2, H, a_count, cap, 3, H, gw3, H, gb3, name="mlp_l3_bwd_w")
+            ops.gemm_nt(dout, 4, w3, H, 1, None, dh2, H, h2, H, a_count, cap, H, 3, 0, name="mlp_l3_bwd_x")
+        else:
+            mid, ldm, nv = ws["mid"], ws["ldm"], ws["nv"]
+            ops.gemm_tn(dout, 4, mid, ldm, a_count, cap, 3, ldm, gw3, ldm, gb3, name="mlp_l3_bwd_w")
+            ops.gemm_nt(dout, 4, w3, ldm, 1, None, dh2, H, mid, ldm, a_count, cap, H, 3, 0, name="mlp_l3_bwd_x",
+                        w_off=nv, mask_off=nv)
+        ops.gemm_tn(dh2, H, h1, H, a_count, cap, H, H, gw2, H, gb2, name="mlp_l2_bwd_w")
+        ops.gemm_nt(dh2, H, w2, H, 1, None, dh1, H, h1, H, a_count, cap, H, H, 0, name="mlp_l2_bwd_x")
+        ops.gemm_tn(dh1, H, x, ldi, a_count, cap, H, in_dim, gw1, in_dim, gb1, name="mlp_l1_bwd_w")
+        # the encoded input is dead after dW1: reuse its buffer for its own gradient
+        ops.gemm_nt(dh1, H, w1, in_dim, 1, None, x, ldi, None, 0, a_count, cap, in_dim, H, 0, name="mlp_l1_bwd_x")
+        mode = 0 if cfg.shading == "MLP_Fea" else 1
+        ops.pe_encode(1, F, cfg.fea_pe, cfg.view_pe, mode, cfg.fea_prog, cfg.view_prog, cfg.n_samples, cfg.ndc,
+                      feat, ldf, None, None, None, a_count, cap, dfeat, ldf, None, 0, x, ldi)
+        return dfeat, [gw1, gb1, gw2, gb2, gw3, gb3]
+
+
+class VMRender(torch.autograd.Function):
+    """rgb_map, depth_map, opacity = render(rays, factors, basis, head).
+
+    Inputs after cfg: rays_o [N,3], rays_d [N,3], aux (jitter [N] | NDC depth
+    table [S] | None), 6 density factors (3 planes, 3 lines), 6 appearance
+    factors, basis weight, then the head parameters (w1,b1,w2,b2,w3,b3) or none
+    for SH. Factors are logical [1,C,H,W] / [1,C,L,1] tensors in channel-last
+    memory (B200_VMSplit stores its parameters that way)."""
+
+    @staticmethod
+    def forward(ctx, cfg, rays_o, rays_d, aux, *tensors):
+        ops._need_cuda(rays_o, "rays_o")
+        lib = _lib.lib()
+        dev = rays_o.device
+        rays_o = rays_o.detach().contiguous().float()
+        rays_d = rays_d.detach().contiguous().float()
+        dens, app, basis_w, head = tensors[0:6], tensors[6:12], tensors[12], tensors[13:]
+        head = [t.detach().contiguous() for t in head]
+        basis_w = basis_w.detach().contiguous()
+        dfs = FactorSet([t.detach() for t in dens[:3]], [t.detach() for t in dens[3:]])
+        afs = FactorSet([t.detach() for t in app[:3]], [t.detach() for t in app[3:]])
+        N, S = rays_o.shape[0], cfg.n_samples
+        F = cfg.app_dim
+        ldf = _r4(F)
+        if basis_w.shape != (F, afs.ctot):
+            raise _lib.JtError(f"basis_mat weight {tuple(basis_w.shape)} != ({F}, {afs.ctot})")
+
+        comp = ops.march_compact(rays_o, rays_d, aux, cfg.ndc, S, cfg.h_geom, cfg.mask)
+        cap = comp.cap
+        sigfeat = torch.empty((cap,), device=dev)
+        ops.vm_gather_fwd(0, dfs, comp.samp, None, comp.count, cap, sigfeat)
+
+        weight = torch.empty((cap,), device=dev)
+        trans = torch.empty((cap,), device=dev)
+        acc = torch.empty((N,), device=dev)
+        wz = torch.empty((N,), device=dev)
+        app_cnt = torch.empty((N,), device=dev, dtype=torch.int32)
+        app_off = torch.zeros((N + 1,), device=dev, dtype=torch.int32)
+        aidx = torch.empty((cap,), device=dev, dtype=torch.int32)
+        app_of = torch.empty((cap,), device=dev, dtype=torch.int32)
+        with TIMER.span("alpha_fwd"):
+            check(lib.jt_alpha_fwd(_p(comp.ray_off), N, _p(sigfeat), _p(comp.dist), _p(comp.samp),
+                                   float(cfg.density_shift), cfg.act, float(cfg.distance_scale), float(cfg.thres),
+                                   _p(weight), _p(trans), _p(acc), _p(wz), _p(app_cnt), _p(app_off), _p(aidx),
+                                   _p(app_of), _stream()), "jt_alpha_fwd")
+        a_count = app_off[N:N + 1]
+
+        comps = torch.empty((cap, afs.ctot), device=dev)
+        ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
+        feat = torch.empty((cap, ldf), device=dev)
+        ops.gemm_nt(comps, afs.ctot, basis_w, afs.ctot, 0, None, feat, ldf, None, 0, a_count, cap, F, afs.ctot, 0,
+                    name="basis_fwd")
+        ws = {}
+        rgb = _Head.forward(cfg, ws, feat, ldf, aidx, comp.sidx, rays_d, a_count, cap, head, dev)
+
+        rgb_pre = torch.empty((N, 3), device=dev)
+        rgb_map = torch.empty((N, 3), device=dev)
+        depth = torch.empty((N,), device=dev)
+        opacity = torch.empty((N,), device=dev)
+        with TIMER.span("composite_fwd"):
+            check(lib.jt_composite_fwd(_p(app_off), N, _p(aidx), _p(weight), _p(rgb), _p(acc), _p(wz), _p(rays_d),
+                                       int(cfg.white_bg), float(cfg.depth_bias), _p(rgb_pre), _p(rgb_map),
+                                       _p(depth), _p(opacity), _stream()), "jt_composite_fwd")
+
+        ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws = cfg, comp, dfs, afs, ws
+        ctx.bufs = dict(rays_d=rays_d, sigfeat=sigfeat, weight=weight, trans=trans, app_off=app_off, aidx=aidx,
+                        app_of=app_of, comps=comps, feat=feat, rgb=rgb, rgb_pre=rgb_pre, basis_w=basis_w, head=head,
+                        a_count=a_count)
+        ctx.n_head = len(head)
+        ctx.mark_non_differentiable(depth)
+        ctx.aux = dict(valid_count=comp.count, app_count=a_count, sidx=comp.sidx, aidx=aidx)
+        return rgb_map, depth, opacity
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_acc):
+        lib = _lib.lib()
+        cfg, comp, dfs, afs, ws, b = ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws, ctx.bufs
+        dev = g_rgb.device
+        N, cap = comp.n_rays, comp.cap
+        F = cfg.app_dim
+        ldf = _r4(F)
+        g_rgb = g_rgb.contiguous().float()
+        g_acc = g_acc.contiguous().float() if g_acc is not None else None
+        shade_act = 2 if cfg.shading == "SH" else 1
+
+        dout = torch.empty((cap, 4), device=dev)
+        dsig = torch.empty((cap,), device=dev)
+        dnorm = torch.empty((N,), device=dev) if cfg.ndc else None
+        with TIMER.span("render_bwd"):
+            check(lib.jt_render_bwd(_p(comp.ray_off), N, _p(b["sigfeat"]), _p(comp.dist), _p(b["weight"]),
+                                    _p(b["trans"]), _p(b["app_of"]), _p(b["rgb"]), _p(b["rgb_pre"]), _p(g_rgb),
+                                    _p(g_acc), float(cfg.density_shift), cfg.act, float(cfg.distance_scale),
+                                    int(cfg.white_bg), shade_act, _p(dout), _p(dsig), _p(dnorm), _stream()),
+                  "jt_render_bwd")
+
+        # one flat zero-filled bucket for all 12 factor gradients (one memset; also the
+        # unit the data-parallel all-reduce works on)
+        shapes = [p.shape for p in dfs.planes] + [l.shape for l in dfs.lines] + \
+                 [p.shape for p in afs.planes] + [l.shape for l in afs.lines]
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        flat = torch.zeros((sum(sizes),), device=dev)
+        views, o = [], 0
+        for s, n in zip(shapes, sizes):
+            views.append(flat[o:o + n].view(s))
+            o += n
+        gdp, gdl, gap, gal = views[0:3], views[3:6], views[6:9], views[9:12]
+
+        dsamp = torch.empty((cap, 4), device=dev)
+        ops.vm_gather_bwd(0, dfs, gdp, gdl, comp.samp, None, comp.count, cap, dsig, dsamp, 0)
+
+        dfeat, head_grads = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
+                                           b["a_count"], cap, b["head"], dev)
+        g_basis = torch.zeros_like(b["basis_w"])
+        ops.gemm_tn(dfeat, ldf, b["comps"], afs.ctot, b["a_count"], cap, F, afs.ctot, g_basis, afs.ctot, None,
+                    name="basis_bwd_w")
+        dcomps = torch.empty((cap, afs.ctot), device=dev)
+        ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
+                    afs.ctot, F, 0, name="basis_bwd_x")
+        ops.vm_gather_bwd(1, afs, gap, gal, comp.samp, b["aidx"], b["a_count"], cap, dcomps, dsamp, 1)
+
+        d_o = torch.empty((N, 3), device=dev)
+        d_d = torch.empty((N, 3), device=dev)
+        with TIMER.span("ray_bwd"):
+            check(lib.jt_ray_bwd(_p(comp.ray_off), N, _p(comp.samp), _p(dsamp), _p(b["rays_d"]), _p(dnorm),
+                                 cfg.h_inv, _p(d_o), _p(d_d), _stream()), "jt_ray_bwd")
+
+        gdpn, gdln = FactorSet.grads_as_nchw(gdp, gdl)
+        gapn, galn = FactorSet.grads_as_nchw(gap, gal)
+        VMRender.last_grad_bucket = flat
+        return (None, d_o, d_d, None, *gdpn, *gdln, *gapn, *galn, g_basis, *head_grads)
+
+
+VMRender.last_grad_bucket = None

@@ -1,0 +1,562 @@
+"""B200_VMSplit -- drop-in for the reference field classes `BAT_VMSplit` /
+`TensorVMSplit` (model/tensorf_repr/bateRF.py:7, tensoRF.py:145).
+
+Same constructor, parameter names / logical shapes (so reference checkpoints
+load), `forward` signature and maintenance methods as the reference
+(SURVEY.md section 8b); selected by the reference engine with
+`--arch.tensorf.model=B200_VMSplit` (model/tensorf.py:375). The hot path runs in
+csrc/*.cu through the C ABI; VM factors are stored channel-last in memory
+(logical shape stays [1,C,H,W]) so the kernels gather whole channel vectors.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import floats, ints
+from .ops import MAT_MODE, VEC_MODE
+from .render import RenderCfg, VMRender
+
+CL = torch.channels_last
+
+
+# ------------------------------------------------------------------ blur taps (host side, 65 numbers)
+def gaussian_taps(t, kernel_size):
+    """reference model/kernels.py:16-22 (taps clamped to <= 1, not normalised)."""
+    ns = torch.arange(-(kernel_size // 2), kernel_size // 2 + 1, dtype=torch.float32)
+    tt = max(t, 0.0001)
+    q = ns / tt
+    k = 1 / (tt * math.sqrt(2 * math.pi)) * torch.exp(-0.5 * q * q)
+    return torch.clamp(k, max=1.0)
+
+
+def average_taps(t, kernel_size):
+    """reference model/kernels.py:24-41 (box filter blended between floor/ceil widths)."""
+    if kernel_size % 2 == 0:
+        kernel_size += 1
+    t = float(t)
+    half = kernel_size // 2
+    out = torch.zeros(kernel_size)
+    for width, wgt in ((min(math.floor(t), half), 1 - t % 1.0), (min(math.ceil(t), half), t % 1.0)):
+        box = torch.zeros(kernel_size)
+        box[half - width:half + width + 1] = 1 / (width * 2 + 1)
+        out = out + wgt * box
+    return out
+
+
+# ------------------------------------------------------------------ occupancy mask
+class AlphaGridMask(torch.nn.Module):
+    """Binary occupancy volume (reference tensorBase.py:80-98) + its bit-packed
+    device copy used by the ray-march kernel."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        super().__init__()
+        self.device = device
+        self.aabb = aabb.to(device)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:]).to(device)
+        d, h, w = self.alpha_volume.shape[-3:]
+        self.gridSize = torch.LongTensor([w, h, d]).to(device)
+        self._pack()
+
+    def _pack(self):
+        d, h, w = self.alpha_volume.shape[-3:]
+        flat = (self.alpha_volume.reshape(-1) > 0).to(torch.int64)
+        pad = (-flat.numel()) % 32
+        if pad:
+            flat = torch.cat([flat, flat.new_zeros(pad)])
+        words = (flat.view(-1, 32) << torch.arange(32, device=flat.device)).sum(-1)
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+        self.bits = words.contiguous()
+        self.h_dims = ints([w, h, d])
+        self.h_geom = floats(self.aabb[0].tolist() + self.invgridSize.tolist())
+
+    def sample_alpha(self, xyz_sampled):
+        """1.0 where the trilinear lookup of the reference would be > 0, else 0.0."""
+        xyz = xyz_sampled.reshape(-1, 3).contiguous().float()
+        n = xyz.shape[0]
+        # a degenerate "ray" per point: o = xyz, d = 0, one sample at depth 0 (NDC table of one entry)
+        ztab = torch.zeros((1,), device=xyz.device)
+        big = floats([-3e38] * 3 + [3e38] * 3 + [1.0] * 3 + [0.0, 0.0, 0.0])
+        _, _, keep = ops.sample_ray_dense(xyz, torch.zeros_like(xyz), ztab, True, 1, big, self)
+        return keep.view(-1).float()
+
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
+
+
+# ------------------------------------------------------------------ shading heads (parameter containers)
+class MLPRender_Fea(torch.nn.Module):
+    """Parameter layout of reference MLPRender_Fea (tensorBase.py:101-114): mlp.{0,2,4}."""
+
+    def __init__(self, in_chanel, viewpe=6, feape=6, featureC=128):
+        super().__init__()
+        self.in_mlpC = 2 * viewpe * 3 + 2 * feape * in_chanel + 3 + in_chanel
+        self.viewpe, self.feape = viewpe, feape
+        self.mlp = torch.nn.Sequential(torch.nn.Linear(self.in_mlpC, featureC), torch.nn.ReLU(inplace=True),
+                                       torch.nn.Linear(featureC, featureC), torch.nn.ReLU(inplace=True),
+                                       torch.nn.Linear(featureC, 3))
+        torch.nn.init.constant_(self.mlp[-1].bias, 0)
+
+    def head_params(self):
+        m = self.mlp
+        return [m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias]
+
+
+class MLPRender_Fea_WeakView(torch.nn.Module):
+    """Parameter layout of reference MLPRender_Fea_WeakView (tensorBase.py:180-196)."""
+
+    def __init__(self, in_chanel, viewpe=6, feape=6, featureC=128):
+        super().__init__()
+        self.in_mlpC = (2 * feape + 1) * in_chanel
+        self.mid_mlpC = 2 * viewpe * 3
+        self.viewpe, self.feape = viewpe, feape
+        self.layer1 = torch.nn.Linear(self.in_mlpC, featureC)
+        self.layer2 = torch.nn.Linear(featureC, featureC)
+        self.layer3 = torch.nn.Linear(featureC + self.mid_mlpC, 3)
+        torch.nn.init.constant_(self.layer3.bias, 0)
+
+    def head_params(self):
+        return [self.layer1.weight, self.layer1.bias, self.layer2.weight, self.layer2.bias,
+                self.layer3.weight, self.layer3.bias]
+
+
+_OPT_FLAGS = ("abs_components", "component_wise_feature2density", "plane_feature2density", "convolve_plane_only",
+              "convolve_positive_only", "ignore_negative_split")
+
+
+class B200_VMSplit(torch.nn.Module):
+    def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
+                 shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,
+                 alphaMask_thres=0.001, distance_scale=25, rayMarch_weight_thres=0.0001, pos_pe=6, view_pe=6,
+                 fea_pe=6, featureC=128, step_ratio=2.0, fea2denseAct="softplus", dtype=torch.float32,
+                 volume_init_scale=0.1, volume_init_bias=0.1):
+        super().__init__()
+        if dtype != torch.float32:
+            raise _lib.JtError("B200_VMSplit keeps fp32 master factors (dtype must be torch.float32)")
+        self.device = device
+        self.dtype = dtype
+        self.alphaMask = alphaMask
+        self.matMode = [list(m) for m in MAT_MODE]
+        self.vecMode = list(VEC_MODE)
+        self.comp_w = [1, 1, 1]
+        self.kernel_density = None
+        self.kernel_color = None
+        self.c2f_mode = None
+        self.reset(aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
+                   distance_scale, rayMarch_weight_thres, fea2denseAct, near_far, step_ratio, shadingMode, pos_pe,
+                   view_pe, fea_pe, featureC, volume_init_scale, volume_init_bias)
+
+    # ---------------------------------------------------------------- construction (tensorBase.py:426-488)
+    def reset(self, aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
+              distance_scale, rayMarch_weight_thres, fea2denseAct, near_far, step_ratio, shadingMode, pos_pe,
+              view_pe, fea_pe, featureC, volume_init_scale, volume_init_bias):
+        def comps(c):
+            return [int(c)] * 3 if isinstance(c, (int, np.integer)) else [int(v) for v in c]
+        self.density_n_comp = comps(density_n_comp)
+        self.app_n_comp = comps(appearance_n_comp)
+        self.app_dim = app_dim
+        self.aabb = torch.as_tensor(aabb, dtype=self.dtype).clone().to(self.device)
+        self.density_shift = density_shift
+        self.alphaMask_thres = alphaMask_thres
+        self.distance_scale = distance_scale
+        self.rayMarch_weight_thres = rayMarch_weight_thres
+        self.fea2denseAct = fea2denseAct
+        self.near_far = near_far
+        self.step_ratio = step_ratio
+        self.update_stepSize(gridSize)
+        self.volume_init_scale = volume_init_scale
+        self.volume_init_bias = volume_init_bias
+        self.init_svd_volume(gridSize[0], self.device, init_scale=volume_init_scale, init_bias=volume_init_bias)
+        self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = shadingMode, pos_pe, view_pe, fea_pe, featureC
+        self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, self.device)
+
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        if shadingMode == "MLP_Fea":
+            self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        elif shadingMode == "MLP_Fea_WeakView":
+            self.renderModule = MLPRender_Fea_WeakView(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        elif shadingMode == "SH":
+            if self.app_dim != 27:
+                raise _lib.JtError("SH shading needs app_dim == 27 (3 x 9 degree-2 coefficients)")
+            self.renderModule = None
+        else:
+            raise Exception(f"Unrecognized / unsupported shading module {shadingMode!r} "
+                            "(B200 path implements MLP_Fea, MLP_Fea_WeakView, SH)")
+
+    def update_stepSize(self, gridSize):
+        """tensorBase.py:477-488, evaluated with torch fp32 exactly as the reference
+        (the resulting floats feed the bit-exact ray-march kernel)."""
+        aabb = self.aabb.detach().cpu().float()
+        size = aabb[1] - aabb[0]
+        g = torch.LongTensor([int(v) for v in gridSize])
+        units = size / (g - 1)
+        step = torch.mean(units) * self.step_ratio
+        diag = torch.sqrt(torch.sum(torch.square(size)))
+        self.aabbSize = size.to(self.device)
+        self.invaabbSize = (2.0 / size).to(self.device)
+        self.gridSize = g.to(self.device)
+        self.units = units.to(self.device)
+        self.stepSize = step.to(self.device)
+        self.aabbDiag = diag.to(self.device)
+        self.nSamples = int((diag / step).item()) + 1
+        # host copies (no device->host reads on the hot path)
+        self._grid = [int(v) for v in g.tolist()]
+        self._h_aabb = aabb
+        self._h_inv = 2.0 / size
+        self._h_step = step
+        self._blur_scale = torch.mean(g / size)            # batBase.py:14
+        self._ztab_cache = {}
+
+    def init_svd_volume(self, res, device, init_density=True, init_app=True, init_basis=True, init_scale=0.1,
+                        init_bias=0.1):
+        if init_density:
+            self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, self._grid, init_scale, init_bias, device)
+        if init_app:
+            self.app_plane, self.app_line = self.init_one_svd(self.app_n_comp, self._grid, init_scale, init_bias, device)
+        if init_basis:
+            self.basis_mat = torch.nn.Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def init_one_svd(self, n_component, gridSize, scale, bias, device):
+        """|bias + scale*N(0,1)| factors (tensoRF.py:159-169), stored channel-last."""
+        planes, lines = [], []
+        for i in range(3):
+            m0, m1 = MAT_MODE[i]
+            p = torch.abs(bias + scale * torch.randn((1, n_component[i], gridSize[m1], gridSize[m0])))
+            l = torch.abs(bias + scale * torch.randn((1, n_component[i], gridSize[VEC_MODE[i]], 1)))
+            planes.append(torch.nn.Parameter(_to_cl(p.to(device))))
+            lines.append(torch.nn.Parameter(_to_cl(l.to(device))))
+        return torch.nn.ParameterList(planes), torch.nn.ParameterList(lines)
+
+    # ---------------------------------------------------------------- small reference helpers
+    def normalize_coord(self, xyz_sampled):
+        return (xyz_sampled - self.aabb[0]) * self.invaabbSize - 1
+
+    def feature2density(self, density_features):
+        if self.fea2denseAct == "softplus":
+            return F.softplus(density_features + self.density_shift)
+        elif self.fea2denseAct == "relu":
+            return F.relu(density_features + self.density_shift)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        groups = [{"params": self.density_line, "lr": lr_init_spatialxyz},
+                  {"params": self.density_plane, "lr": lr_init_spatialxyz},
+                  {"params": self.app_line, "lr": lr_init_spatialxyz},
+                  {"params": self.app_plane, "lr": lr_init_spatialxyz},
+                  {"params": self.basis_mat.parameters(), "lr": lr_init_network}]
+        if isinstance(self.renderModule, torch.nn.Module):
+            groups += [{"params": self.renderModule.parameters(), "lr": lr_init_network}]
+        return groups
+
+    def freeze_scene(self, opt=None):
+        self._set_scene_grad(False)
+
+    def unfreeze_scene(self, opt=None):
+        self._set_scene_grad(True)
+
+    def _set_scene_grad(self, flag):
+        self.basis_mat.weight.requires_grad = flag
+        if isinstance(self.renderModule, torch.nn.Module):
+            self.renderModule.requires_grad_(flag)
+        for plist in (self.density_plane, self.density_line, self.app_plane, self.app_line):
+            for p in plist:
+                p.requires_grad = flag
+
+    def density_L1(self):
+        total = 0
+        for i in range(3):
+            total = total + torch.mean(torch.abs(self.density_plane[i])) + torch.mean(torch.abs(self.density_line[i]))
+        return total
+
+    def TV_loss_density(self, reg):
+        return sum(reg(self.density_plane[i]) * 1e-2 for i in range(3))
+
+    def TV_loss_app(self, reg):
+        return sum(reg(self.app_plane[i]) * 1e-2 for i in range(3))
+
+    # ---------------------------------------------------------------- geometry blobs for the C ABI
+    def _h_geom(self):
+        near, far = self.near_far
+        near32 = float(torch.tensor(float(near), dtype=torch.float32))
+        far32 = float(torch.tensor(float(far), dtype=torch.float32))
+        return floats(self._h_aabb[0].tolist() + self._h_aabb[1].tolist() + self._h_inv.tolist() +
+                      [float(self._h_step), near32, far32])
+
+    def _mask(self):
+        return self.alphaMask if self.alphaMask is not None else None
+
+    def _ndc_table(self, n_samples, is_train):
+        """linspace(near, far, S) built with torch on the CPU (bit-identical to the
+        oracle), cached; stratified jitter added on the device (tensorBase.py:556-559)."""
+        near, far = float(self.near_far[0]), float(self.near_far[1])
+        key = (near, far, n_samples)
+        z = self._ztab_cache.get(key)
+        if z is None:
+            if len(self._ztab_cache) > 64:
+                self._ztab_cache.clear()
+            z = torch.linspace(near, far, n_samples, dtype=torch.float32).to(self.device)
+            self._ztab_cache[key] = z
+        if is_train:
+            z = z + torch.rand_like(z) * ((far - near) / n_samples)
+        return z
+
+    # ---------------------------------------------------------------- K1 API
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1, jitter=None):
+        """tensorBase.py:572-612 -> (rays_pts [N,S,3], interpx [N,S], valid [N,S])."""
+        n_samples = N_samples if N_samples > 0 else self.nSamples
+        aux = None
+        if is_train:
+            aux = jitter if jitter is not None else torch.rand((rays_o.shape[0],), device=rays_o.device)
+            aux = aux.reshape(-1).contiguous().float()
+        return ops.sample_ray_dense(rays_o.detach().contiguous().float(), rays_d.detach().contiguous().float(), aux,
+                                    False, n_samples, self._h_geom(), None)
+
+    def sample_ray_ndc(self, rays_o, rays_d, is_train=True, N_samples=-1, simulate_euclid_sample=False,
+                       simulate_euclid_depth=False, ndc_near_plane=1.0, jitter=None):
+        """tensorBase.py:554-571 (simulate_euclid_* are False in every shipped config)."""
+        if simulate_euclid_sample or simulate_euclid_depth:
+            raise _lib.JtError("ndc_simulate_euclid_* is not supported by the B200 path (False in all reference configs)")
+        n_samples = N_samples if N_samples > 0 else self.nSamples
+        z = self._ndc_table(n_samples, is_train and jitter is None)
+        if is_train and jitter is not None:
+            near, far = float(self.near_far[0]), float(self.near_far[1])
+            z = z + jitter.reshape(-1).to(z) * ((far - near) / n_samples)
+        pts, zz, valid = ops.sample_ray_dense(rays_o.detach().contiguous().float(),
+                                              rays_d.detach().contiguous().float(), z.contiguous(), True, n_samples,
+                                              self._h_geom(), None)
+        return pts, z.unsqueeze(0), valid
+
+    # ---------------------------------------------------------------- K5 API
+    def get_kernel(self, opt, c2f_mode, c2f_parameter, c2f_kernel_size=25):
+        """BatBase.get_kernel (batBase.py:13-25): taps on the device, computed on the host."""
+        t = self._blur_scale * float(c2f_parameter)
+        if c2f_mode == "uniform-gaussian":
+            k = gaussian_taps(t, c2f_kernel_size)
+        elif c2f_mode == "uniform-average":
+            k = average_taps(t, c2f_kernel_size)
+        else:
+            raise RuntimeError(f"invalid c2f_mode {c2f_mode}")
+        return k.to(device=self.device, dtype=torch.float32)
+
+    def convolute_line(self, kernel, line):
+        return ops.BlurFactor.apply(line, kernel.reshape(-1).contiguous(), line.shape[2], 1, 2)
+
+    def convolute_plane(self, kernel, plane, H, W):
+        return ops.BlurFactor.apply(plane, kernel.reshape(-1).contiguous(), int(H), int(W), 3)
+
+    def _blurred(self, planes, lines, kernel):
+        """All six factors of one group, blurred (bateRF.py:64-78 / 105-118)."""
+        if kernel is None:
+            return list(planes), list(lines)
+        bp, bl = [], []
+        for i in range(3):
+            m0, m1 = MAT_MODE[i]
+            bp.append(self.convolute_plane(kernel, planes[i], self._grid[m0], self._grid[m1]))
+            bl.append(self.convolute_line(kernel, lines[i]))
+        return bp, bl
+
+    # ---------------------------------------------------------------- K2 API
+    def compute_densityfeature(self, xyz_sampled, kernel=None, c2f_mode=None, interp_mode="bilinear"):
+        """bateRF.py:41-94 / tensoRF.py:230-251: [V,3] normalised coords -> [V]."""
+        self._check_interp(interp_mode)
+        planes, lines = self._blurred(self.density_plane, self.density_line, kernel if c2f_mode is not None else None)
+        return ops.DensityFeature.apply(xyz_sampled.reshape(-1, 3), *planes, *lines)
+
+    def compute_appfeature(self, xyz_sampled, kernel=None, c2f_mode=None, interp_mode="bilinear"):
+        """bateRF.py:97-130 / tensoRF.py:254-270: [A,3] -> [A, app_dim]."""
+        self._check_interp(interp_mode)
+        planes, lines = self._blurred(self.app_plane, self.app_line, kernel if c2f_mode is not None else None)
+        comps = ops.AppComponents.apply(xyz_sampled.reshape(-1, 3), *planes, *lines)
+        return ops.Linear.apply(comps, self.basis_mat.weight, None)
+
+    @staticmethod
+    def _check_interp(mode):
+        if mode != "bilinear":
+            raise _lib.JtError(f"grid_sample_interp_mode={mode!r}: only 'bilinear' is implemented (all reference configs)")
+
+    def compute_alpha(self, xyz_locs, length=1):
+        """BatBase.compute_alpha (batBase.py:27-42); reuses the density kernel cached by the last forward."""
+        if self.alphaMask is not None:
+            alpha_mask = self.alphaMask.sample_alpha(xyz_locs) > 0
+        else:
+            alpha_mask = torch.ones_like(xyz_locs[:, 0], dtype=bool)
+        sigma = torch.zeros(xyz_locs.shape[:-1], device=xyz_locs.device)
+        xyz = self.normalize_coord(xyz_locs[alpha_mask])
+        if xyz.shape[0] > 0:
+            feat = self.compute_densityfeature(xyz, self.kernel_density, self.c2f_mode)
+            sigma[alpha_mask] = self.feature2density(feat)
+        return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
+
+    # ---------------------------------------------------------------- forward (batBase.py:44-165)
+    def forward(self, opt, center, ray_dir, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
+                c2f_parameter_density=None, c2f_parameter_color=None, c2f_mode=None, c2f_kernel_size=None,
+                is_test_optim=False, view_pe_progress=1.0, fea_pe_progress=1.0, jitter=None, bg_coin=None):
+        """Returns (rgb_map [N,3], depth_map [N], opacity [N]); differentiable w.r.t.
+        the field parameters and `center` / `ray_dir` (joint pose optimisation).
+
+        Extra keyword-only knobs (not in the reference, used by the parity tests):
+        `jitter` replaces the stratified-sampling random numbers, `bg_coin`
+        replaces the train-time background coin flip `torch.rand((1,)) < 0.5`."""
+        self.opt = opt
+        self._check_opt(opt)
+        n_samples = N_samples if N_samples > 0 else self.nSamples
+        dev = center.device
+
+        blur_active = c2f_parameter_density is not None or c2f_parameter_color is not None
+        self.c2f_mode = c2f_mode
+        if c2f_mode is not None:
+            dmode = "uniform-gaussian" if is_test_optim else c2f_mode
+            self.kernel_density = self.get_kernel(opt, dmode, c2f_parameter_density, c2f_kernel_size)
+            self.kernel_color = self.get_kernel(opt, c2f_mode, c2f_parameter_color, c2f_kernel_size)
+        else:
+            self.kernel_density = None
+            self.kernel_color = None
+
+        if ndc_ray:
+            if opt.camera.ndc_simulate_euclid_sample or opt.camera.ndc_simulate_euclid_depth:
+                raise _lib.JtError("ndc_simulate_euclid_* is not supported by the B200 path")
+            aux = self._ndc_table(n_samples, is_train and jitter is None)
+            if is_train and jitter is not None:
+                near, far = float(self.near_far[0]), float(self.near_far[1])
+                aux = aux + jitter.reshape(-1).to(aux) * ((far - near) / n_samples)
+            aux = aux.contiguous()
+        elif is_train:
+            aux = jitter if jitter is not None else torch.rand((center.shape[0],), device=dev)
+            aux = aux.reshape(-1).contiguous().float()
+        else:
+            aux = None
+
+        # same short-circuit as batBase.py:154, so the host RNG stream is consumed identically
+        white = bool(white_bg or (is_train and (bool(torch.rand((1,)) < 0.5) if bg_coin is None else bool(bg_coin))))
+
+        cfg = RenderCfg(
+            n_samples=int(n_samples), ndc=bool(ndc_ray), white_bg=white, h_geom=self._h_geom(),
+            h_inv=floats(self._h_inv.tolist()),
+            mask=(self.alphaMask if (self.alphaMask is not None and not blur_active) else None),   # batBase.py:76
+            density_shift=float(self.density_shift), act=(0 if self.fea2denseAct == "softplus" else 1),
+            distance_scale=float(self.distance_scale), thres=float(self.rayMarch_weight_thres),
+            depth_bias=-float(self.near_far[0]) + 0.05, shading=self.shadingMode, app_dim=int(self.app_dim),
+            fea_pe=int(self.fea_pe), view_pe=int(self.view_pe), hidden=int(self.featureC),
+            fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress))
+
+        dp, dl = self._blurred(self.density_plane, self.density_line, self.kernel_density)
+        ap, al = self._blurred(self.app_plane, self.app_line, self.kernel_color)
+        head = self.renderModule.head_params() if self.renderModule is not None else []
+        return VMRender.apply(cfg, center.reshape(-1, 3), ray_dir.reshape(-1, 3), aux, *dp, *dl, *ap, *al,
+                              self.basis_mat.weight, *head)
+
+    render = forward      # north_star calls the entry point `render`; the reference engine calls forward
+
+    def _check_opt(self, opt):
+        arch = opt.arch
+        for f in _OPT_FLAGS:
+            if getattr(arch, f, False):
+                raise _lib.JtError(f"opt.arch.{f}=True is not implemented by the B200 path (False in all reference configs)")
+        sh = arch.shading
+        if not (sh.detach_viewdirs and sh.detach_xyz):
+            raise _lib.JtError("the B200 path implements detach_viewdirs/detach_xyz = True (all reference configs)")
+        if getattr(sh, "predict_density", False):
+            raise _lib.JtError("shading.predict_density is not implemented by the B200 path")
+        self._check_interp(arch.tensorf.grid_sample_interp_mode)
+        if self.fea2denseAct not in ("softplus", "relu"):
+            raise _lib.JtError(f"fea2denseAct {self.fea2denseAct!r} unsupported")
+
+    # ---------------------------------------------------------------- maintenance (between steps)
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        """tensoRF.py:274-295: bilinear align_corners=True resize of every factor."""
+        res_target = [int(v) for v in res_target]
+        for planes, lines in ((self.app_plane, self.app_line), (self.density_plane, self.density_line)):
+            for i in range(3):
+                m0, m1 = MAT_MODE[i]
+                planes[i] = torch.nn.Parameter(_to_cl(F.interpolate(
+                    planes[i].data, size=(res_target[m1], res_target[m0]), mode="bilinear", align_corners=True)))
+                lines[i] = torch.nn.Parameter(_to_cl(F.interpolate(
+                    lines[i].data, size=(res_target[VEC_MODE[i]], 1), mode="bilinear", align_corners=True)))
+        self.update_stepSize(res_target)
+
+    @torch.no_grad()
+    def getDenseAlpha(self, gridSize=None):
+        """tensorBase.py:618-633."""
+        gridSize = self._grid if gridSize is None else [int(v) for v in gridSize]
+        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gridSize[0]), torch.linspace(0, 1, gridSize[1]),
+                                             torch.linspace(0, 1, gridSize[2]), indexing="ij"), -1).to(self.device)
+        dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
+        alpha = torch.zeros_like(dense_xyz[..., 0])
+        for i in range(gridSize[0]):
+            alpha[i] = self.compute_alpha(dense_xyz[i].view(-1, 3), self.stepSize).view((gridSize[1], gridSize[2]))
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def updateAlphaMask(self, gridSize=(200, 200, 200)):
+        """tensorBase.py:635-661: dense alpha -> max_pool3d(5) -> threshold -> new aabb."""
+        gridSize = [int(v) for v in gridSize]
+        alpha, dense_xyz = self.getDenseAlpha(gridSize)
+        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
+        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+        alpha = F.max_pool3d(alpha, kernel_size=5, padding=2, stride=1).view(gridSize[::-1])
+        alpha = (alpha >= self.alphaMask_thres).to(alpha.dtype)
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
+        valid_xyz = dense_xyz[alpha > 0.5]
+        return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+
+    @torch.no_grad()
+    def shrink(self, new_aabb):
+        """tensoRF.py:297-334: crop every factor to the voxel range covering new_aabb."""
+        xyz_min, xyz_max = new_aabb
+        t_l = torch.round((xyz_min - self.aabb[0]) / self.units).long()
+        b_r = torch.round((xyz_max - self.aabb[0]) / self.units).long() + 1
+        b_r = torch.stack([b_r, self.gridSize]).amin(0)
+        tl, br = t_l.tolist(), b_r.tolist()
+        for i in range(3):
+            v = VEC_MODE[i]
+            m0, m1 = MAT_MODE[i]
+            for lines in (self.density_line, self.app_line):
+                lines[i] = torch.nn.Parameter(_to_cl(lines[i].data[..., tl[v]:br[v], :]))
+            for planes in (self.density_plane, self.app_plane):
+                planes[i] = torch.nn.Parameter(_to_cl(planes[i].data[..., tl[m1]:br[m1], tl[m0]:br[m0]]))
+        if not torch.all(self.alphaMask.gridSize == self.gridSize):
+            lo, hi = t_l / (self.gridSize - 1), (b_r - 1) / (self.gridSize - 1)
+            corrected = torch.zeros_like(new_aabb)
+            corrected[0] = (1 - lo) * self.aabb[0] + lo * self.aabb[1]
+            corrected[1] = (1 - hi) * self.aabb[0] + hi * self.aabb[1]
+            new_aabb = corrected
+        self.aabb = new_aabb
+        new_size = b_r - t_l
+        self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
+
+    # ---------------------------------------------------------------- checkpoint side-state (tensorBase.py:508-552)
+    def get_reset_kwargs(self):
+        return {"aabb": self.aabb, "gridSize": list(self._grid), "density_n_comp": self.density_n_comp,
+                "appearance_n_comp": self.app_n_comp, "app_dim": self.app_dim, "density_shift": self.density_shift,
+                "alphaMask_thres": self.alphaMask_thres, "distance_scale": self.distance_scale,
+                "rayMarch_weight_thres": self.rayMarch_weight_thres, "fea2denseAct": self.fea2denseAct,
+                "near_far": self.near_far, "step_ratio": self.step_ratio, "shadingMode": self.shadingMode,
+                "pos_pe": self.pos_pe, "view_pe": self.view_pe, "fea_pe": self.fea_pe, "featureC": self.featureC,
+                "volume_init_scale": self.volume_init_scale, "volume_init_bias": self.volume_init_bias}
+
+    def save_param_state(self):
+        ckpt = {"tensorf_reset_kwargs": self.get_reset_kwargs()}
+        if self.alphaMask is not None:
+            vol = self.alphaMask.alpha_volume.bool().cpu().numpy()
+            ckpt.update({"alphaMask.shape": vol.shape, "alphaMask.mask": np.packbits(vol.reshape(-1)),
+                         "alphaMask.aabb": self.alphaMask.aabb.cpu()})
+        return ckpt
+
+    def load_param_state(self, ckpt):
+        if "alphaMask.aabb" in ckpt.keys():
+            length = np.prod(ckpt["alphaMask.shape"])
+            vol = torch.from_numpy(np.unpackbits(ckpt["alphaMask.mask"])[:length].reshape(ckpt["alphaMask.shape"]))
+            self.alphaMask = AlphaGridMask(self.device, ckpt["alphaMask.aabb"].to(self.device), vol.float().to(self.device))
+        self.reset(**ckpt["tensorf_reset_kwargs"])
+
+
+def _to_cl(x):
+    """Force channel-last physical layout ([H][W][C]) for a [1,C,H,W] tensor, also for
+    degenerate shapes where torch's channels_last stride check is ambiguous."""
+    n, c, h, w = x.shape
+    buf = x.permute(0, 2, 3, 1).contiguous()
+    return buf.permute(0, 3, 1, 2)

@@ -1,0 +1,64 @@
+"""world_size-2 gloo test of the ray-sharding + flat-bucket gradient all-reduce logic."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from joint_tensorf_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    # a channel-last "plane", a line and a dense weight, identical on both ranks
+    plane = torch.nn.Parameter(torch.randn(1, 8, 6, 5).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    line = torch.nn.Parameter(torch.randn(1, 8, 7, 1))
+    w = torch.nn.Parameter(torch.randn(3, 4))
+    bucket = parallel.GradBucket([plane, line, w])
+    bucket.attach()
+    # every rank "renders" its shard of 10 rays: loss = sum over its rays
+    rays = torch.arange(10, dtype=torch.float32)
+    (mine,) = parallel.shard_rays(rays, rays, rank, world)[:1]
+    loss = (plane.sum() + 2 * line.sum() + 3 * w.sum()) * mine.sum()
+    loss.backward()
+    assert plane.grad.data_ptr() == bucket.views[0].data_ptr(), "autograd must accumulate into the bucket"
+    assert plane.grad.stride() == plane.stride()
+    bucket.all_reduce(average=False)
+    total = float(rays.sum())
+    ok = (torch.allclose(plane.grad, torch.full_like(plane, total)) and
+          torch.allclose(line.grad, torch.full_like(line, 2 * total)) and
+          torch.allclose(w.grad, torch.full_like(w, 3 * total)))
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert parallel.frames_of_rank(10, 1, 4) == [1, 5, 9]
+
+
+def test_gradient_bucket_allreduce_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]

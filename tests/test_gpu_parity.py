@@ -1,0 +1,173 @@
+"""GPU parity against golden vectors of the live reference and against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): valid masks / sample indices bit-exact;
+rgb, depth, opacity <= 1e-4 max-abs (fp32); gradients <= 1e-4 max-abs AND
+<= 1e-3 of the largest gradient entry (the relative bound is the one that bites,
+SURVEY.md A.12; fp32 atomics reorder sums)."""
+import pytest
+import torch
+
+import joint_tensorf_b200 as jt
+from common import (field_from_golden, golden_names, golden_valid, load_golden, rel_err,
+                    render_kwargs_from_golden, vo)
+from gpu_common import default_opt, forward_kwargs, module_from_golden, run_module_on_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ABS_TOL = 1e-4
+GRAD_REL_TOL = 1e-3
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_sample_mask_and_indices_bit_exact(name):
+    g = load_golden(name)
+    m = module_from_golden(g, DEV)
+    case = g["case"]
+    ndc = case.get("ndc", False)
+    o, d = g["rays_o"].to(DEV), g["rays_d"].to(DEV)
+    jit = g["jitter"].to(DEV) if g["jitter"] is not None else None
+    if ndc:
+        pts, z, valid = m.sample_ray_ndc(o, d, is_train=case["train"], N_samples=g["n_samples"], jitter=jit)
+    else:
+        pts, z, valid = m.sample_ray(o, d, is_train=case["train"], N_samples=g["n_samples"], jitter=jit)
+    ref_valid = golden_valid(g)
+    if g["mask_volume"] is None or case["blur"] is not None:
+        assert torch.equal(valid.cpu(), ref_valid), f"{int((valid.cpu() != ref_valid).sum())} mask bits differ"
+    assert torch.equal(z.cpu().expand_as(g["z"]), g["z"]), "sample depths differ bitwise"
+    # compacted list == nonzero(mask), including the alpha-mask cull
+    geom = m._h_geom()
+    aux = None
+    if ndc:
+        aux = (m._ndc_table(g["n_samples"], False) + (jit.reshape(-1) * (2.0 / g["n_samples"]) if jit is not None else 0)).contiguous()
+    elif jit is not None:
+        aux = jit.reshape(-1).contiguous()
+    mask = m.alphaMask if (m.alphaMask is not None and case["blur"] is None) else None
+    comp = jt.ops.march_compact(o.contiguous(), d.contiguous(), aux, ndc, g["n_samples"], geom, mask)
+    v = int(comp.count.item())
+    assert v == g["valid_count"]
+    want = torch.nonzero(ref_valid.reshape(-1)).reshape(-1).to(torch.int32)
+    assert torch.equal(comp.sidx[:v].cpu(), want)
+    off = comp.ray_off.cpu()
+    assert torch.equal(off[1:] - off[:-1], ref_valid.sum(-1).to(torch.int32))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_backward_matches_reference_golden(name):
+    g = load_golden(name)
+    out = run_module_on_golden(g, DEV)
+    assert (out["rgb"].cpu() - g["rgb"]).abs().max() <= ABS_TOL
+    assert (out["acc"].cpu() - g["acc"]).abs().max() <= ABS_TOL
+    assert (out["depth"].cpu() - g["depth"]).abs().max() <= ABS_TOL
+    assert rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]) <= GRAD_REL_TOL
+    assert rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]) <= GRAD_REL_TOL
+    for k, ref in g["grads"].items():
+        got = out["grads"][k].cpu()
+        assert got.shape == ref.shape, k
+        assert rel_err(got, ref) <= GRAD_REL_TOL, (k, rel_err(got, ref))
+    for k, (s, sabs, mx) in g["grad_sums"].items():
+        got = out["grads"][k].double().abs().sum().item()
+        assert abs(got - sabs) <= 1e-3 * max(sabs, 1e-12), (k, got, sabs)
+
+
+@pytest.mark.parametrize("blur", [None, (0.1, 0.15)])
+def test_midsize_against_oracle(blur):
+    """128^3 (cfg1 shape), 256 rays: CUDA path vs the CPU oracle on identical inputs."""
+    kw, run = jt.synth.config("cfg1")
+    torch.manual_seed(0)
+    m = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), DEV, **kw)
+    with torch.no_grad():
+        for i in range(3):
+            m.density_plane[i].mul_(4.0)
+            m.density_line[i].mul_(4.0)
+    o, d, _ = jt.synth.blender_rays(256, 8, seed=3)
+    S = run["n_samples"]
+    jit = torch.rand(256, 1, generator=torch.Generator().manual_seed(9))
+    params = {k: v.detach().cpu().contiguous().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    field = vo.Field(aabb=m.aabb.cpu(), grid=[128] * 3, params=params, near_far=[2.0, 6.0], step_ratio=0.5,
+                     density_shift=-10.0, distance_scale=25.0, weight_thres=1e-6, act="softplus", shading="MLP_Fea")
+    okw = dict(n_samples=S, white_bg=True, jitter=jit)
+    fkw = dict(white_bg=True, is_train=True, N_samples=S, jitter=jit.to(DEV), bg_coin=False)
+    if blur:
+        okw.update(blur_mode="uniform-gaussian", blur_density=blur[0], blur_color=blur[1], kernel_size=64)
+        fkw.update(c2f_mode="uniform-gaussian", c2f_parameter_density=blur[0], c2f_parameter_color=blur[1],
+                   c2f_kernel_size=64)
+    oc, dc = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    rgb_ref, depth_ref, acc_ref = vo.render(field, oc, dc, **okw)
+    w = torch.rand(256, 3, generator=torch.Generator().manual_seed(4))
+    (rgb_ref * w).sum().backward()
+    og, dg = o.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    rgb, depth, acc = m.forward(default_opt(), og, dg, **fkw)
+    (rgb * w.to(DEV)).sum().backward()
+    assert (rgb.cpu() - rgb_ref).abs().max() <= ABS_TOL
+    assert (acc.cpu() - acc_ref).abs().max() <= ABS_TOL
+    assert (depth.cpu() - depth_ref).abs().max() <= ABS_TOL
+    assert rel_err(og.grad.cpu(), oc.grad) <= GRAD_REL_TOL
+    assert rel_err(dg.grad.cpu(), dc.grad) <= GRAD_REL_TOL
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad.cpu(), params[k].grad) <= GRAD_REL_TOL, k
+
+
+def test_full_size_cfg2_properties():
+    """300^3 / 4096 rays / S=1000 (the benchmark workload): size-independent invariants."""
+    kw, run = jt.synth.config("cfg2")
+    torch.manual_seed(0)
+    m = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), DEV, **kw)
+    with torch.no_grad():
+        for i in range(3):
+            m.density_plane[i].mul_(3.0)
+            m.density_line[i].mul_(3.0)
+    o, d, _ = jt.synth.blender_rays(4096, 32)
+    o, d = o.to(DEV), d.to(DEV)
+    S = run["n_samples"]
+    jit = torch.rand(4096, device=DEV)
+    # (1) compaction: sorted, unique, per-ray counts == dense mask popcount
+    pts, z, valid = m.sample_ray(o, d, is_train=True, N_samples=S, jitter=jit)
+    comp = jt.ops.march_compact(o, d, jit.contiguous(), False, S, m._h_geom(), None)
+    v = int(comp.count.item())
+    assert v == int(valid.sum())
+    sidx = comp.sidx[:v]
+    assert bool((sidx[1:] > sidx[:-1]).all())
+    assert torch.equal(sidx.long(), torch.nonzero(valid.reshape(-1)).reshape(-1))
+    assert 0.5 < v / (4096 * S) < 0.8
+    # (2) render: weights + background transmittance partition unity; rgb in [0,1]
+    og, dg = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    rgb, depth, acc = m.forward(default_opt(), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit)
+    assert bool(((rgb >= 0) & (rgb <= 1)).all()) and bool(((acc >= -1e-5) & (acc <= 1 + 1e-4)).all())
+    assert torch.isfinite(depth).all()
+    # (3) linearity of the backward pass in the upstream gradient
+    w1, w2 = torch.rand_like(rgb), torch.rand_like(rgb)
+    params = [m.density_plane[0], m.app_line[1], m.basis_mat.weight]
+    ga = torch.autograd.grad((rgb * w1).sum(), params + [og], retain_graph=True)
+    gb = torch.autograd.grad((rgb * w2).sum(), params + [og], retain_graph=True)
+    gc = torch.autograd.grad((rgb * (w1 + 2 * w2)).sum(), params + [og])
+    for a, b, c in zip(ga, gb, gc):
+        assert rel_err(a + 2 * b, c) <= 1e-3
+    # (4) directional finite difference on the ray origins (pose gradient path), fp32-limited
+    with torch.no_grad():
+        dirv = torch.randn_like(o)
+        eps = 1e-3
+        kwf = dict(white_bg=True, is_train=True, N_samples=S, jitter=jit)
+        lp = (m.forward(default_opt(), o + eps * dirv, d, **kwf)[0] * w1).sum().double()
+        lm = (m.forward(default_opt(), o - eps * dirv, d, **kwf)[0] * w1).sum().double()
+    fd = float((lp - lm) / (2 * eps))
+    an = float((ga[3] * dirv).sum())
+    assert abs(fd - an) <= 0.05 * max(abs(an), abs(fd), 1e-3), (fd, an)
+
+
+def test_empty_and_degenerate_batches():
+    g = load_golden("cubic_blur")
+    m = module_from_golden(g, DEV)
+    opt = default_opt()
+    # rays that miss the box entirely: no valid sample, white background
+    o = torch.tensor([[10.0, 10.0, 10.0], [0.0, 0.0, 8.0]], device=DEV)
+    d = torch.tensor([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0]], device=DEV).requires_grad_(True)
+    rgb, depth, acc = m.forward(opt, o, d, white_bg=True, is_train=False, N_samples=64)
+    assert torch.equal(acc, torch.zeros_like(acc)) and torch.equal(rgb, torch.ones_like(rgb))
+    rgb.sum().backward()
+    assert torch.equal(d.grad, torch.zeros_like(d.grad))
+    # a single ray, a ragged count (not a multiple of the warp size)
+    o1, d1 = g["rays_o"][:1].to(DEV), g["rays_d"][:1].to(DEV)
+    r1 = m.forward(opt, o1, d1, white_bg=True, is_train=False, N_samples=g["n_samples"])[0]
+    o37, d37 = g["rays_o"][:37].to(DEV), g["rays_d"][:37].to(DEV)
+    r37 = m.forward(opt, o37, d37, white_bg=True, is_train=False, N_samples=g["n_samples"])[0]
+    assert torch.allclose(r1, r37[:1], atol=1e-6)

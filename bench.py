@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s forward+backward of the TensoRF-VM render hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (own arm, B200 kernels)
+    python bench.py --impl reference --gpus N ...            (reference arm: CPU port)
+
+Workload (BASELINE.json configs[1], "cfg2"): TensoRF-VM 300^3 grid, density 3x16 /
+appearance 3x48 components, app_dim 27, MLP_Fea shading head, 4096-ray batch, S=1000
+samples per ray, forward + backward to all factor / head / ray gradients. Synthetic
+Blender-shaped rays and random-init factors (joint_tensorf_b200.synth).
+
+A step = pose-independent part of one training iteration: stratified jitter ->
+forward -> MSE -> backward (+ one NCCL all-reduce of the flat gradient bucket when
+N > 1). The optimizer step is excluded (SURVEY.md section 8d timing protocol).
+N > 1 is weak scaling: every rank renders its own 4096 rays.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays/sec fwd+bwd (300^3 VM, 4096-ray batch)"
+UNIT = "rays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--rays", type=int, default=4096)
+    ap.add_argument("--blur", type=float, default=0.0, help="c2f blur parameter (0 = off, cfg3 uses 0.15)")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU port (oracle) timing
+def oracle_field(workload, seed=0):
+    from joint_tensorf_b200 import synth
+    from oracle import vm_oracle as vo
+    kw, run = synth.config(workload)
+    params = vo.init_params(kw["gridSize"], kw["density_n_comp"], kw["appearance_n_comp"], kw["app_dim"],
+                            kw["shadingMode"], kw["featureC"], kw["view_pe"], kw["fea_pe"],
+                            kw["volume_init_scale"], kw["volume_init_bias"], seed=seed)
+    for v in params.values():
+        v.requires_grad_(True)
+    field = vo.Field(aabb=torch.tensor(kw["aabb"]), grid=kw["gridSize"], params=params, near_far=kw["near_far"],
+                     step_ratio=kw["step_ratio"], density_shift=float(kw["density_shift"]),
+                     distance_scale=kw["distance_scale"], weight_thres=kw["rayMarch_weight_thres"],
+                     act=kw["fea2denseAct"], shading=kw["shadingMode"], view_pe=kw["view_pe"], fea_pe=kw["fea_pe"])
+    return field, run
+
+
+def time_cpu_port(workload, n_rays, steps, warmup, blur):
+    """Reference algorithm (oracle port, same ATen CPU operators as the reference) on
+    the host cores: forward + MSE + backward on a bounded sample of the workload."""
+    from joint_tensorf_b200 import synth
+    from oracle import vm_oracle as vo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    field, run = oracle_field(workload)
+    o, d, _ = synth.blender_rays(n_rays, max(1, min(32, n_rays // 16)), seed=1)
+    target = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(2))
+    kw = dict(n_samples=run["n_samples"], white_bg=run["white_bg"], ndc=run["ndc"])
+    if blur > 0:
+        kw.update(blur_mode="uniform-gaussian", blur_density=blur * 0.6, blur_color=blur, kernel_size=64)
+    times = []
+    for it in range(warmup + steps):
+        oc, dc = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        jit = torch.rand(n_rays, 1)
+        for p in field.params.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        rgb, _, _ = vo.render(field, oc, dc, jitter=jit, **kw)
+        loss = ((rgb - target) ** 2).mean()
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return n_rays / sec, sec, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_rays
+    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    rps, sec, cores = time_cpu_port(args.workload, n, steps, warm, args.blur)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, S=1000, "
+                               f"{n}-ray sample of the 4096-ray batch, fwd+bwd", "blur": args.blur},
+        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} of 4096 rays per step, {steps} steps, oracle/vm_oracle.py (torch CPU, "
+                                   f"{cores} threads)"},
+        "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- own arm
+def algorithmic_bytes(name, V, A, cd, ca, ctot_a):
+    """bytes a kernel must move per launch (fp32 factors)."""
+    s = 4
+    dens_f = V * (18 * cd * s + 16)                 # 3 x (4+2) taps x C_d x 4 B + coords in + feature out
+    app_f = A * (18 * ca * s + 12 + 4 * ctot_a)     # taps + coords + component row out (un-fused)
+    table = {
+        "vm_density_fwd": dens_f,
+        "vm_app_fwd": app_f,
+        "vm_density_bwd": V * (3 * 18 * cd * s + 4 + 16),
+        "vm_app_bwd": A * (3 * 18 * ca * s + 4 * ctot_a + 16),
+    }
+    return table.get(name)
+
+
+def gemm_flops(name, A, F, ctot, in_dim, H):
+    table = {
+        "basis_fwd": 2 * A * F * ctot, "basis_bwd_x": 2 * A * F * ctot, "basis_bwd_w": 2 * A * F * ctot,
+        "mlp_l1_fwd": 2 * A * in_dim * H, "mlp_l1_bwd_x": 2 * A * in_dim * H, "mlp_l1_bwd_w": 2 * A * in_dim * H,
+        "mlp_l2_fwd": 2 * A * H * H, "mlp_l2_bwd_x": 2 * A * H * H, "mlp_l2_bwd_w": 2 * A * H * H,
+        "mlp_l3_fwd": 2 * A * H * 3, "mlp_l3_bwd_x": 2 * A * H * 3, "mlp_l3_bwd_w": 2 * A * H * 3,
+    }
+    return table.get(name)
+
+
+def own_arm(args):
+    import torch.distributed as dist
+
+    import joint_tensorf_b200 as jt
+    from joint_tensorf_b200 import ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured" if peaks else "fallback"
+
+    kw, run = jt.synth.config(args.workload)
+    kw = dict(kw)
+    torch.manual_seed(0)                       # identical replicas on every rank
+    model = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), dev, **kw)
+    from joint_tensorf_b200.options import default_opt
+    opt = default_opt(model.shadingMode, run["ndc"])
+    N, S = args.rays, run["n_samples"]
+    o_h, d_h, _ = jt.synth.blender_rays(N, 32, seed=1 + rank)
+    tgt_h = torch.rand(N, 3, generator=torch.Generator().manual_seed(100 + rank))
+    o_h, d_h, tgt_h = o_h.pin_memory(), d_h.pin_memory(), tgt_h.pin_memory()
+    o_d, d_d, tgt_d = o_h.to(dev), d_h.to(dev), tgt_h.to(dev)
+    loss_h = torch.empty((), pin_memory=True)
+    fkw = dict(white_bg=run["white_bg"], is_train=True, ndc_ray=run["ndc"], N_samples=S)
+    if args.blur > 0:
+        fkw.update(c2f_mode="uniform-gaussian", c2f_parameter_density=args.blur * 0.6,
+                   c2f_parameter_color=args.blur, c2f_kernel_size=64)
+    params = [p for p in model.parameters()]
+    bucket = parallel.GradBucket(params) if world > 1 else None
+
+    def step(o, d, tgt):
+        if bucket is not None:
+            bucket.zero()
+            bucket.attach()
+        else:
+            for p in params:
+                p.grad = None
+        o = o.requires_grad_(True)
+        d = d.requires_grad_(True)
+        rgb, depth, acc = model(opt, o, d, **fkw)
+        loss = ((rgb - tgt) ** 2).mean()
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce(average=True)
+        return loss
+
+    def step_e2e():
+        o = o_h.to(dev, non_blocking=True)
+        d = d_h.to(dev, non_blocking=True)
+        t = tgt_h.to(dev, non_blocking=True)
+        loss = step(o, d, t)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # > 126 MB L2
+
+    def timed(fn, k):
+        tot = 0.0
+        for _ in range(k):
+            flush.fill_(1.0)                                           # evict L2 between steps (untimed)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            tot += s.elapsed_time(e)
+        return tot
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(o_d.clone(), d_d.clone(), tgt_d)
+    barrier()
+    l0 = jt._lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(lambda: step(o_d.clone(), d_d.clone(), tgt_d), args.steps)
+        barrier()
+    launches = jt._lib.launch_count() - l0
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    roof, breakdown = None, None
+    if rank == 0 and not args.no_breakdown:
+        ops.TIMER.enabled = True
+        for _ in range(3):
+            step(o_d.clone(), d_d.clone(), tgt_d)
+        ops.TIMER.summary()
+        reps = 5
+        for _ in range(reps):
+            flush.fill_(1.0)
+            step(o_d.clone(), d_d.clone(), tgt_d)
+        summ = ops.TIMER.summary()
+        ops.TIMER.enabled = False
+        V, A = (int(t.item()) for t in jt.VMRender.last_counts)      # measured on the last step's batch
+        breakdown = {k: round(v[0] / reps, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1][0])}
+        top = next(iter(breakdown))
+        cd, ca = model.density_n_comp[0], model.app_n_comp[0]
+        F_, H_ = model.app_dim, model.featureC
+        in_dim = F_ + 3 + 2 * model.fea_pe * F_ + 6 * model.view_pe
+        per_launch_ms = summ[top][0] / summ[top][1]
+        by = algorithmic_bytes(top, V, A, cd, ca, sum(model.app_n_comp))
+        fl = gemm_flops(top, A, F_, sum(model.app_n_comp), in_dim, H_)
+        if by is not None:
+            ach = by / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": per_launch_ms}
+        elif fl is not None:
+            ach = fl / (per_launch_ms * 1e-3) / 1e12
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": per_launch_ms}
+        gather = sum(breakdown.get(k, 0.0) for k in ("vm_density_fwd", "vm_app_fwd", "vm_density_bwd", "vm_app_bwd"))
+        gbytes = sum(algorithmic_bytes(k, V, A, cd, ca, sum(model.app_n_comp))
+                     for k in ("vm_density_fwd", "vm_app_fwd", "vm_density_bwd", "vm_app_bwd"))
+        if roof is not None and gather > 0:
+            roof["vm_gather_fwd_bwd"] = {"ms": gather, "achieved": gbytes / (gather * 1e-3) / 1e9,
+                                         "frac": gbytes / (gather * 1e-3) / 1e9 / hbm_peak, "V": V, "A": A}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, sec, cores = time_cpu_port(args.workload, args.cpu_rays, 2, 1, args.blur)
+        cpu = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_rays} of {N} rays, 2 timed fwd+bwd iterations of oracle/vm_oracle.py "
+                         f"(torch CPU, {cores} threads)"}
+
+    if rank == 0:
+        rays_total = N * world
+        h2d = (o_h.numel() + d_h.numel() + tgt_h.numel()) * 4
+        line = {
+            "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, "
+                                   f"S={S}, {N} rays/GPU, fwd+bwd, optimizer step excluded",
+                       "blur": args.blur, "l2": "256 MB write between timed steps (L2 flushed)",
+                       "parallelism": f"ray-sharded x{world}, NCCL all-reduce of a flat fp32 gradient bucket"},
+            "e2e": {"value": rays_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if breakdown is not None:
+            line["kernel_ms_per_step"] = breakdown
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        own_arm(a)

@@ -194,7 +194,7 @@ class VMRender(torch.autograd.Function):
                         a_count=a_count)
         ctx.n_head = len(head)
         ctx.mark_non_differentiable(depth)
-        ctx.aux = dict(valid_count=comp.count, app_count=a_count, sidx=comp.sidx, aidx=aidx)
+        VMRender.last_counts = (comp.count, a_count)      # device scalars V, A (diagnostics / bench)
         return rgb_map, depth, opacity
 
     @staticmethod
@@ -257,3 +257,4 @@ class VMRender(torch.autograd.Function):
 
 
 VMRender.last_grad_bucket = None
+VMRender.last_counts = None

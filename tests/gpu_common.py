@@ -5,22 +5,7 @@ import joint_tensorf_b200 as jt
 from common import render_kwargs_from_golden  # noqa: F401
 
 
-class _NS(dict):
-    def __getattr__(self, k):
-        try:
-            v = self[k]
-        except KeyError:
-            raise AttributeError(k)
-        return _NS(v) if isinstance(v, dict) else v
-
-
-def default_opt(shading="MLP_Fea", ndc=False):
-    """The opt fields the field layer reads per forward (batBase.py:46-62)."""
-    return _NS(arch=dict(abs_components=False, component_wise_feature2density=False, plane_feature2density=False,
-                         convolve_plane_only=False, convolve_positive_only=False, ignore_negative_split=False,
-                         ndc_near_plane=1.0, shading=dict(model=shading, detach_viewdirs=True, detach_xyz=True),
-                         tensorf=dict(grid_sample_interp_mode="bilinear")),
-               camera=dict(ndc=ndc, ndc_simulate_euclid_sample=False, ndc_simulate_euclid_depth=False), nerf=dict())
+from joint_tensorf_b200.options import default_opt  # noqa: F401,E402
 
 
 def module_from_golden(g, device="cuda:0"):

@@ -115,6 +115,22 @@ int jt_sh_shade(int bwd, const float* feat, int ldf, const int* aidx, const int*
                 int n_samples, int normalize_dir, const int* n_dev, int n_max, float* rgb, const float* dout,
                 float* dfeat, int ldd, cudaStream_t stream);
 
+/* ---- K3, tensor-core path (tcgen05.mma + TMEM) ---------------------------- */
+/* Plumbing self test: mode 0  D[128][N] = A[128][K] * B[N][K]^T (K-major smem operands);
+ * mode 1  D[m][n] = sum_s X[s][m] * Y[s][n] with X = A [128][Ma], Y = B [128][N]
+ * (MN-major operands, the form the weight-gradient GEMMs use). bf16 products, fp32 sums. */
+int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, float* D, int K, int N, int Ma,
+                   cudaStream_t stream);
+/* basis_mat (tensoRF.py:270) + positional_encoding (tensorBase.py:43-55) + MLPRender_Fea
+ * (tensorBase.py:116-126) fused per tile of 128 appearance samples, app_dim 27 / hidden 64 /
+ * fea_pe = view_pe = 2: comps [A][144] -> rgb [A][4]. split = 1: bf16 operands; split = 2:
+ * every operand as hi+lo bf16 terms, 3 MMAs per product (fp32-class accuracy). feat_out
+ * (optional) [A][28] receives the basis projection. */
+int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* sidx, const float* rays_d,
+                   int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
+                   const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
+                   float fea_progress, float view_progress, float* rgb, float* feat_out, cudaStream_t stream);
+
 /* ---- K4: alpha compositing --------------------------------------------- */
 /* feature2density (tensorBase.py:696-700; act 0 softplus, 1 relu) + raw2alpha
  * (tensorBase.py:57-65) over the compacted samples of each ray, then the app_mask

@@ -23,6 +23,8 @@ SIGNATURES = {
     "jt_gemm_tn": [_P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _P],
     "jt_pe_encode": [_I, _I, _I, _I, _I, _F, _F, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _P],
     "jt_sh_shade": [_I, _P, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P],
+    "jt_tc_selftest": [_I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
+    "jt_head_fwd_tc": [_I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],
     "jt_alpha_fwd": [_P, _I, _P, _P, _P, _F, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_composite_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P],
     "jt_render_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _I, _I, _P, _P, _P, _P],

@@ -1,0 +1,408 @@
+// K3 (tensor-core path) -- basis_mat projection + positional encoding + MLP_Fea
+// shading head as ONE kernel on the 5th-generation tensor cores (tcgen05.mma,
+// accumulators in TMEM), per tile of 128 appearance samples.
+//
+// Replaces reference basis_mat (tensoRF.py:156,270 / bateRF.py:130),
+// positional_encoding (tensorBase.py:43-55) and MLPRender_Fea.forward
+// (tensorBase.py:116-126) for app_dim 27 / hidden 64 / pe 2 (the Blender configs).
+//
+// Per tile: thread t owns sample row t (and TMEM lane t).
+//   comps row (144 fp32, global) -> bf16 tile A0 (smem)        MMA1: feat  = A0 * Wb^T   [128x32]
+//   feat (tcgen05.ld) -> PE -> bf16 tile A1 [128x160]           MMA2: h1    = A1 * W1^T   [128x64]
+//   relu(h1) -> bf16 tile A2 [128x80]                           MMA3: h2    = A2 * W2^T   [128x64]
+//   relu(h2) -> layer 3 (3x64 dot products in registers) -> sigmoid -> rgb
+// Biases ride in the GEMMs: column 150 of A1 and column 64 of A2 are 1.0 and the
+// staged weights carry b1 / b2 in those columns.
+// SPLIT = 2 stores every operand as hi + lo bf16 terms and issues 3 MMAs
+// (hi*hi + hi*lo + lo*hi): ~2^-16 relative product error, i.e. fp32-class results
+// from bf16 tensor-core throughput. SPLIT = 1 is plain bf16.
+#include "jt_common.cuh"
+#include "tc_common.cuh"
+#include "../../include/jt_vm.h"
+
+namespace jt {
+using namespace tc;
+
+constexpr int TM = 128;                    // samples per tile == threads per CTA
+constexpr int F_ = 27, NB = 32;            // app_dim, padded N of the basis GEMM
+constexpr int CT = 144;                    // sum of appearance components
+constexpr int IN_ = 150, K1 = 160;         // encoded input (reference order) / padded tensor-core order
+constexpr int BIAS1 = 30;                  // tensor-core column order of layer 1 (any K permutation is a valid GEMM):
+                                           //   0..26 feat | 27..29 dir | 30 = 1.0 (bias) | 31 = 0 |
+                                           //   32+4e..35+4e = [sin x, sin 2x, cos x, cos 2x] of element e
+                                           //   (e < 27: feat e, e >= 27: dir e-27) | 152..159 = 0
+// reference column (tensorBase.py:116-122 concatenation order) of tensor-core column c; -1 zero, -2 bias
+__host__ __device__ constexpr int ref_col_l1(int c) {
+    if (c < F_ + 3) return c;
+    if (c == BIAS1) return -2;
+    if (c < 32 || c >= 152) return -1;
+    const int cc = c - 32, e = cc >> 2, r = cc & 3;
+    return e < F_ ? (F_ + 3) + 4 * e + r : (F_ + 3) + 4 * F_ + 4 * (e - F_) + r;
+}
+constexpr int H_ = 64, K2 = 80;            // hidden, padded K of layer 2 (col 64 = 1 -> bias)
+
+__host__ __device__ constexpr int tile_bytes(int rows, int cols) { return rows * cols * 2; }
+
+// ------------------------------------------------------------------ generic staging helpers
+// W (n, k) fp32 row-major [N][ldw] -> canonical bf16 tile of NR rows x KP cols. `kmap` selects the
+// source column of tile column k: 0 identity (k == bias_col takes bias[n]), 1 layer-1 tensor-core order.
+__device__ void stage_weight(unsigned char* hi, unsigned char* lo, const float* __restrict__ W, int ldw, int N, int K,
+                             int NR, int KP, const float* __restrict__ bias, int bias_col, int kmap) {
+    for (int idx = threadIdx.x; idx < NR * (KP / 8); idx += blockDim.x) {
+        const int chunk = idx / NR, n = idx - chunk * NR;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = chunk * 8 + i;
+            int src = k < K ? k : (k == bias_col ? -2 : -1);
+            if (kmap == 1) src = ref_col_l1(k);
+            float x = 0.f;
+            if (n < N) {
+                if (src >= 0) x = W[(size_t)n * ldw + src];
+                else if (src == -2 && bias) x = bias[n];
+            }
+            v[i] = x;
+        }
+        store_chunk(hi, lo, NR, chunk, n, v);
+    }
+}
+
+// issue the k-steps of one GEMM: D[128 x N] = A[128 x K] * B[N x K]^T, both K-major tiles.
+template <int SPLIT>
+__device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, const unsigned char* a_hi, const unsigned char* a_lo,
+                                                  const unsigned char* b_hi, const unsigned char* b_lo, int K, int NR,
+                                                  int N) {
+    const uint32_t idesc = idesc_bf16(128, N, 0, 0);
+    const uint32_t a_lbo = TM * 16, b_lbo = NR * 16;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ah = smem_desc(smem_u32(a_hi) + ks * 2 * a_lbo, a_lbo, 128);
+        const uint64_t bh = smem_desc(smem_u32(b_hi) + ks * 2 * b_lbo, b_lbo, 128);
+        mma_bf16(d_tmem, ah, bh, idesc, acc);
+        acc = 1;
+        if (SPLIT == 2) {
+            const uint64_t al = smem_desc(smem_u32(a_lo) + ks * 2 * a_lbo, a_lbo, 128);
+            const uint64_t bl = smem_desc(smem_u32(b_lo) + ks * 2 * b_lbo, b_lbo, 128);
+            mma_bf16(d_tmem, ah, bl, idesc, 1);
+            mma_bf16(d_tmem, al, bh, idesc, 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ self test of the MMA plumbing
+// mode 0: D[128][N] = A[128][K] * B[N][K]^T          (K-major operands)
+// mode 1: D[m][n]   = sum_s X[s][m] * Y[s][n]        (MN-major operands; X [128][Ma], Y [128][N], K = 128 rows)
+__global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float* __restrict__ A, int lda,
+                                                          const float* __restrict__ B, int ldb, float* __restrict__ D,
+                                                          int K, int N, int Ma) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned char* ta = smem;                       // A / X tile: 128 rows x 128 cols max
+    unsigned char* tb = smem + tile_bytes(128, 256);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (mode == 0) {
+        for (int c = 0; c < K / 8; ++c) {           // thread = row of A
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = A[(size_t)tid * lda + c * 8 + i];
+            store_chunk(ta, nullptr, 128, c, tid, v);
+        }
+        stage_weight(tb, nullptr, B, ldb, N, K, N, K, nullptr, -1, 0);
+    } else {
+        for (int c = 0; c < 128 / 8; ++c) {         // X tile padded to 128 columns with zeros
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (c * 8 + i < Ma) ? A[(size_t)tid * lda + c * 8 + i] : 0.f;
+            store_chunk(ta, nullptr, 128, c, tid, v);
+        }
+        for (int c = 0; c < N / 8; ++c) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = B[(size_t)tid * ldb + c * 8 + i];
+            store_chunk(tb, nullptr, 128, c, tid, v);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        if (mode == 0) {
+            issue_gemm_kmajor<1>(tmem, ta, nullptr, tb, nullptr, K, N, N);
+        } else {
+            const uint32_t idesc = idesc_bf16(128, N, 1, 1);
+            for (int ks = 0; ks < 128 / 16; ++ks) {             // K = sample rows, 16 per step = 256 B
+                const uint64_t ad = smem_desc(smem_u32(ta) + ks * 256, 128, 128 * 16);
+                const uint64_t bd = smem_desc(smem_u32(tb) + ks * 256, 128, 128 * 16);
+                mma_bf16(tmem, ad, bd, idesc, ks > 0);
+            }
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (c0 + i < N) D[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------ encoded-input row (tensorBase.py:43-55,116-122)
+// in tensor-core column order (see BIAS1); PE values carry the annealing masks
+// clamp(progress*2 - l, 0, 1).
+struct PEMask { float f0, f1, v0, v1; };
+
+__device__ __forceinline__ void encode_chunk(int chunk, const float feat[32], const float dir[3], const PEMask& pm,
+                                             float v[8]) {
+    if (chunk < 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = chunk * 8 + i;
+            v[i] = c < F_ ? feat[c] : c < F_ + 3 ? dir[c - F_] : c == BIAS1 ? 1.0f : 0.f;
+        }
+    } else if (chunk < 19) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e = (chunk - 4) * 2 + h;
+            const bool is_view = e >= F_;
+            const float src = is_view ? dir[e - F_] : feat[e];
+            float s, co;
+            sincosf(src, &s, &co);
+            const float m0 = is_view ? pm.v0 : pm.f0, m1 = is_view ? pm.v1 : pm.f1;
+            v[4 * h + 0] = s * m0;
+            v[4 * h + 1] = (2.f * s * co) * m1;
+            v[4 * h + 2] = co * m0;
+            v[4 * h + 3] = (1.f - 2.f * s * s) * m1;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------ fused head forward
+template <int SPLIT>
+struct FwdSmem {
+    static constexpr int WB = tile_bytes(NB, CT), W1 = tile_bytes(H_, K1), W2 = tile_bytes(H_, K2);
+    static constexpr int A = tile_bytes(TM, K1);               // A0 / A1 / A2 alias one region
+    static constexpr int off_wb = 0, off_w1 = off_wb + SPLIT * WB, off_w2 = off_w1 + SPLIT * W1;
+    static constexpr int off_a = off_w2 + SPLIT * W2;
+    static constexpr int off_w3 = off_a + SPLIT * A;           // fp32 [3][64] + b3[3]
+    static constexpr int total = off_w3 + (3 * H_ + 4) * 4;
+};
+
+template <int SPLIT>
+__global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
+                                                         const int* __restrict__ sidx, const float* __restrict__ rays_d,
+                                                         int S, int normalize_dir, const float* __restrict__ Wb,
+                                                         const float* __restrict__ W1, const float* __restrict__ b1,
+                                                         const float* __restrict__ W2, const float* __restrict__ b2,
+                                                         const float* __restrict__ W3, const float* __restrict__ b3,
+                                                         const int* __restrict__ n_dev, int n_fixed, float fprog,
+                                                         float vprog, float* __restrict__ rgb, float* __restrict__ feat_out) {
+    using L = FwdSmem<SPLIT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int n = n_dev ? *n_dev : n_fixed;
+
+    unsigned char* wb_hi = smem + L::off_wb;  unsigned char* wb_lo = SPLIT == 2 ? wb_hi + L::WB : nullptr;
+    unsigned char* w1_hi = smem + L::off_w1;  unsigned char* w1_lo = SPLIT == 2 ? w1_hi + L::W1 : nullptr;
+    unsigned char* w2_hi = smem + L::off_w2;  unsigned char* w2_lo = SPLIT == 2 ? w2_hi + L::W2 : nullptr;
+    unsigned char* a_hi = smem + L::off_a;    unsigned char* a_lo = SPLIT == 2 ? a_hi + L::A : nullptr;
+    float* w3s = reinterpret_cast<float*>(smem + L::off_w3);
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    stage_weight(wb_hi, wb_lo, Wb, CT, F_, CT, NB, CT, nullptr, -1, 0);
+    stage_weight(w1_hi, w1_lo, W1, IN_, H_, IN_, H_, K1, b1, BIAS1, 1);
+    stage_weight(w2_hi, w2_lo, W2, H_, H_, H_, H_, K2, b2, H_, 0);
+    for (int i = tid; i < 3 * H_ + 3; i += TM) w3s[i] = i < 3 * H_ ? W3[i] : b3[i - 3 * H_];
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t T_FEAT = 0, T_H1 = 32, T_H2 = 96;
+    uint32_t phase = 0;
+    PEMask pm;
+    pm.f0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f); pm.f1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
+    pm.v0 = fminf(fmaxf(vprog * 2.f - 0.f, 0.f), 1.f); pm.v1 = fminf(fmaxf(vprog * 2.f - 1.f, 0.f), 1.f);
+
+    for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
+        const int row = tile * TM + tid;
+        const bool live = row < n;
+        // ---- A0: component row -> bf16
+        {
+            const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * CT);
+#pragma unroll 3
+            for (int c = 0; c < CT / 8; ++c) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+                if (live) { x = __ldg(src + 2 * c); y = __ldg(src + 2 * c + 1); }
+                const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                store_chunk(a_hi, a_lo, TM, c, tid, v);
+            }
+        }
+        float dir[3] = {0.f, 0.f, 0.f};
+        if (live) {
+            const int ray = sidx[aidx[row]] / S;
+            dir[0] = rays_d[3 * ray]; dir[1] = rays_d[3 * ray + 1]; dir[2] = rays_d[3 * ray + 2];
+            if (normalize_dir) {
+                const float nn = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+                dir[0] /= nn; dir[1] /= nn; dir[2] /= nn;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_kmajor<SPLIT>(tmem + T_FEAT, a_hi, a_lo, wb_hi, wb_lo, CT, NB, NB);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- feat -> encoded input A1
+        float feat[32];
+        tmem_ld32(lane_addr + T_FEAT, feat);
+        if (feat_out && live) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                *reinterpret_cast<float4*>(feat_out + (size_t)row * 28 + 4 * q) =
+                    make_float4(feat[4 * q], feat[4 * q + 1], feat[4 * q + 2], q == 6 ? 0.f : feat[4 * q + 3]);
+        }
+#pragma unroll
+        for (int c = 0; c < K1 / 8; ++c) {
+            float v[8];
+            encode_chunk(c, feat, dir, pm, v);
+            store_chunk(a_hi, a_lo, TM, c, tid, v);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_kmajor<SPLIT>(tmem + T_H1, a_hi, a_lo, w1_hi, w1_lo, K1, H_, H_);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- relu(h1) -> A2 (col 64 = 1 carries b2)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float h[32];
+            tmem_ld32(lane_addr + T_H1 + 32 * half, h);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(h[c * 8 + i], 0.f);
+                store_chunk(a_hi, a_lo, TM, half * 4 + c, tid, v);
+            }
+        }
+        {
+            const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_chunk(a_hi, a_lo, TM, 8, tid, one);
+            store_chunk(a_hi, a_lo, TM, 9, tid, zero);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_kmajor<SPLIT>(tmem + T_H2, a_hi, a_lo, w2_hi, w2_lo, K2, H_, H_);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- relu(h2) -> layer 3 + sigmoid
+        float o0 = w3s[3 * H_], o1 = w3s[3 * H_ + 1], o2 = w3s[3 * H_ + 2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float h[32];
+            tmem_ld32(lane_addr + T_H2 + 32 * half, h);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float x = fmaxf(h[i], 0.f);
+                o0 = fmaf(x, w3s[half * 32 + i], o0);
+                o1 = fmaf(x, w3s[H_ + half * 32 + i], o1);
+                o2 = fmaf(x, w3s[2 * H_ + half * 32 + i], o2);
+            }
+        }
+        if (live)
+            *reinterpret_cast<float4*>(rgb + 4 * (size_t)row) =
+                make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f);
+        // all tcgen05.ld of this tile are complete (wait::ld) before the next tile's MMAs overwrite TMEM
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+    if (bytes > 48 * 1024)
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return JT_ERR_LAUNCH;
+    return JT_OK;
+}
+
+}  // namespace jt
+
+using namespace jt;
+
+extern "C" int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, float* D, int K, int N,
+                              int Ma, cudaStream_t stream) {
+    JT_CHECK_ARG(A && B && D && (mode == 0 || mode == 1));
+    JT_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256 && Ma <= 128);
+    const int smem = tile_bytes(128, 256) * 2;
+    if (int rc = set_smem(tc_selftest_kernel, smem)) return rc;
+    g_launches += 1;
+    tc_selftest_kernel<<<1, 128, smem, stream>>>(mode, A, lda, B, ldb, D, K, N, Ma);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* sidx, const float* rays_d,
+                              int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
+                              const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev,
+                              int n_max, float fea_progress, float view_progress, float* rgb, float* feat_out,
+                              cudaStream_t stream) {
+    JT_CHECK_ARG(comps && aidx && sidx && rays_d && Wb && W1 && b1 && W2 && b2 && W3 && b3 && rgb);
+    JT_CHECK_ARG(split == 1 || split == 2);
+    if (n_max <= 0) return JT_OK;
+    long long tiles = ((long long)n_max + TM - 1) / TM;
+    g_launches += 1;
+    if (split == 1) {
+        const int smem = FwdSmem<1>::total;
+        if (int rc = set_smem(head_fwd_tc_kernel<1>, smem)) return rc;
+        int grid = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+        head_fwd_tc_kernel<1><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1,
+                                                          b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,
+                                                          view_progress, rgb, feat_out);
+    } else {
+        const int smem = FwdSmem<2>::total;
+        if (int rc = set_smem(head_fwd_tc_kernel<2>, smem)) return rc;
+        int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+        head_fwd_tc_kernel<2><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1,
+                                                          b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,
+                                                          view_progress, rgb, feat_out);
+    }
+    JT_RETURN_LAUNCH();
+}

@@ -191,6 +191,23 @@ def sh_shade(bwd, feat, ldf, aidx, sidx, rays_d, n_samples, normalize_dir, n_dev
                                      _stream()), "jt_sh_shade")
 
 
+# ------------------------------------------------------------------ K3 tensor-core path
+def tc_selftest(mode, a, b, k, n, ma=0):
+    d = torch.zeros((128, n), device=a.device)
+    check(_lib.lib().jt_tc_selftest(mode, _p(a), a.shape[1], _p(b), b.shape[1], _p(d), k, n, ma, _stream()),
+          "jt_tc_selftest")
+    return d
+
+
+def head_fwd_tc(split, comps, aidx, sidx, rays_d, n_samples, normalize_dir, wb, w1, b1, w2, b2, w3, b3, n_dev, n_max,
+                fprog, vprog, rgb, feat_out=None):
+    with TIMER.span("head_fwd_tc"):
+        check(_lib.lib().jt_head_fwd_tc(split, _p(comps), _p(aidx), _p(sidx), _p(rays_d), n_samples,
+                                        int(normalize_dir), _p(wb), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
+                                        _p(n_dev), int(n_max), float(fprog), float(vprog), _p(rgb), _p(feat_out),
+                                        _stream()), "jt_head_fwd_tc")
+
+
 # ------------------------------------------------------------------ K5
 def blur_cl(x_phys, h, w, c, taps, axes, adjoint):
     """x_phys: contiguous fp32 buffer holding h*w*c floats, interpreted as [h][w][c]."""

@@ -1,0 +1,46 @@
+"""Print (do not assert) the error of every tensor-core check -- one GPU round trip, full picture."""
+import sys, os, traceback
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+import test_gpu_tc as t
+from joint_tensorf_b200 import ops
+
+for k, n in [(16, 16), (32, 16), (144, 32), (160, 64), (80, 64)]:
+    try:
+        g = torch.Generator().manual_seed(0)
+        a = torch.randn(128, k, generator=g).cuda(); b = torch.randn(n, k, generator=g).cuda()
+        d = ops.tc_selftest(0, a, b, k, n); torch.cuda.synchronize()
+        ref = t._bf(a) @ t._bf(b).T
+        print(f"kmajor K={k} N={n}: max err {float((d-ref).abs().max()):.3e} ref max {float(ref.abs().max()):.3e} "
+              f"frac rows ok {float(((d-ref).abs().max(1).values < 1e-2).float().mean()):.3f} "
+              f"frac cols ok {float(((d-ref).abs().max(0).values < 1e-2).float().mean()):.3f}")
+    except Exception:
+        traceback.print_exc()
+for ma, n in [(64, 80), (32, 144), (8, 80)]:
+    try:
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(128, ma, generator=g).cuda(); y = torch.randn(128, n, generator=g).cuda()
+        d = ops.tc_selftest(1, x, y, 128, n, ma); torch.cuda.synchronize()
+        ref = t._bf(x).T @ t._bf(y)
+        print(f"mnmajor Ma={ma} N={n}: max err {float((d[:ma]-ref).abs().max()):.3e} ref max {float(ref.abs().max()):.3e} "
+              f"pad rows max {float(d[ma:].abs().max()):.3e}")
+    except Exception:
+        traceback.print_exc()
+for split in (1, 2):
+    for a_count in (128, 1000):
+        try:
+            p, comps, rays_d, sidx, aidx, S = t._head_inputs(a_count)
+            ref, feat_ref = t._head_reference(p, comps, rays_d, sidx, aidx, S, 0.8, 0.6)
+            d = {k: v.cuda().contiguous() for k, v in p.items()}
+            rgb = torch.zeros((a_count, 4), device="cuda"); feat = torch.zeros((a_count, 28), device="cuda")
+            cnt = torch.tensor([a_count], device="cuda", dtype=torch.int32)
+            ops.head_fwd_tc(split, comps.cuda(), aidx.cuda(), sidx.cuda(), rays_d.cuda(), S, False,
+                            d["basis_mat.weight"], d["renderModule.mlp.0.weight"], d["renderModule.mlp.0.bias"],
+                            d["renderModule.mlp.2.weight"], d["renderModule.mlp.2.bias"], d["renderModule.mlp.4.weight"],
+                            d["renderModule.mlp.4.bias"], cnt, a_count, 0.8, 0.6, rgb, feat)
+            torch.cuda.synchronize()
+            print(f"head split={split} A={a_count}: feat err {float((feat[:, :27].cpu()-feat_ref).abs().max()):.3e} "
+                  f"rgb err {float((rgb[:, :3].cpu()-ref).abs().max()):.3e}")
+        except Exception:
+            traceback.print_exc()

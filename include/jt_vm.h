@@ -131,6 +131,19 @@ int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* si
                    const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
                    float fea_progress, float view_progress, float* rgb, float* feat_out, cudaStream_t stream);
 
+/* Backward of jt_head_fwd_tc (bf16 tensor-core GEMMs, fp32 accumulation in TMEM): from comps
+ * [A][144] and dout [A][4] (gradient at the head's pre-activation, from jt_render_bwd) computes
+ * dcomps [A][144] (for jt_vm_gather_bwd) and ADDS the weight gradients into gWb [27][144],
+ * gW1 [64][150], gb1, gW2 [64][64], gb2, gW3 [3][64], gb3. Activations are recomputed; `stage`
+ * is scratch of jt_head_bwd_tc_stage_bytes(n_max) bytes (128-byte aligned) holding the bf16
+ * operand tiles between the data-gradient and the weight-gradient kernel. */
+long long jt_head_bwd_tc_stage_bytes(int n_max);
+int jt_head_bwd_tc(const float* comps, const float* dout, const int* aidx, const int* sidx, const float* rays_d,
+                   int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
+                   const float* W2, const float* b2, const float* W3, const int* n_dev, int n_max,
+                   float fea_progress, float view_progress, float* dcomps, void* stage, float* gWb, float* gW1,
+                   float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, cudaStream_t stream);
+
 /* ---- K4: alpha compositing --------------------------------------------- */
 /* feature2density (tensorBase.py:696-700; act 0 softplus, 1 relu) + raw2alpha
  * (tensorBase.py:57-65) over the compacted samples of each ray, then the app_mask

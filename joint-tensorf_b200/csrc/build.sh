@@ -3,6 +3,6 @@
 set -e
 cd "$(dirname "$0")"
 SRCS="lib.cu march.cu vm_gather.cu composite.cu shade.cu blur.cu"
-[ -f shade_tc.cu ] && SRCS="$SRCS shade_tc.cu"
+for f in shade_tc.cu shade_tc_bwd.cu; do [ -f $f ] && SRCS="$SRCS $f"; done
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
      -Xcompiler -fPIC -shared -Xptxas -v "$@" -o libjt_vm.so $SRCS

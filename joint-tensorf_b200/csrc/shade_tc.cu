@@ -16,78 +16,11 @@
 // SPLIT = 2 stores every operand as hi + lo bf16 terms and issues 3 MMAs
 // (hi*hi + hi*lo + lo*hi): ~2^-16 relative product error, i.e. fp32-class results
 // from bf16 tensor-core throughput. SPLIT = 1 is plain bf16.
-#include "jt_common.cuh"
-#include "tc_common.cuh"
+#include "head_tc.cuh"
 #include "../../include/jt_vm.h"
 
 namespace jt {
 using namespace tc;
-
-constexpr int TM = 128;                    // samples per tile == threads per CTA
-constexpr int F_ = 27, NB = 32;            // app_dim, padded N of the basis GEMM
-constexpr int CT = 144;                    // sum of appearance components
-constexpr int IN_ = 150, K1 = 160;         // encoded input (reference order) / padded tensor-core order
-constexpr int BIAS1 = 30;                  // tensor-core column order of layer 1 (any K permutation is a valid GEMM):
-                                           //   0..26 feat | 27..29 dir | 30 = 1.0 (bias) | 31 = 0 |
-                                           //   32+4e..35+4e = [sin x, sin 2x, cos x, cos 2x] of element e
-                                           //   (e < 27: feat e, e >= 27: dir e-27) | 152..159 = 0
-// reference column (tensorBase.py:116-122 concatenation order) of tensor-core column c; -1 zero, -2 bias
-__host__ __device__ constexpr int ref_col_l1(int c) {
-    if (c < F_ + 3) return c;
-    if (c == BIAS1) return -2;
-    if (c < 32 || c >= 152) return -1;
-    const int cc = c - 32, e = cc >> 2, r = cc & 3;
-    return e < F_ ? (F_ + 3) + 4 * e + r : (F_ + 3) + 4 * F_ + 4 * (e - F_) + r;
-}
-constexpr int H_ = 64, K2 = 80;            // hidden, padded K of layer 2 (col 64 = 1 -> bias)
-
-__host__ __device__ constexpr int tile_bytes(int rows, int cols) { return rows * cols * 2; }
-
-// ------------------------------------------------------------------ generic staging helpers
-// W (n, k) fp32 row-major [N][ldw] -> canonical bf16 tile of NR rows x KP cols. `kmap` selects the
-// source column of tile column k: 0 identity (k == bias_col takes bias[n]), 1 layer-1 tensor-core order.
-__device__ void stage_weight(unsigned char* hi, unsigned char* lo, const float* __restrict__ W, int ldw, int N, int K,
-                             int NR, int KP, const float* __restrict__ bias, int bias_col, int kmap) {
-    for (int idx = threadIdx.x; idx < NR * (KP / 8); idx += blockDim.x) {
-        const int chunk = idx / NR, n = idx - chunk * NR;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = chunk * 8 + i;
-            int src = k < K ? k : (k == bias_col ? -2 : -1);
-            if (kmap == 1) src = ref_col_l1(k);
-            float x = 0.f;
-            if (n < N) {
-                if (src >= 0) x = W[(size_t)n * ldw + src];
-                else if (src == -2 && bias) x = bias[n];
-            }
-            v[i] = x;
-        }
-        store_chunk(hi, lo, NR, chunk, n, v);
-    }
-}
-
-// issue the k-steps of one GEMM: D[128 x N] = A[128 x K] * B[N x K]^T, both K-major tiles.
-template <int SPLIT>
-__device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, const unsigned char* a_hi, const unsigned char* a_lo,
-                                                  const unsigned char* b_hi, const unsigned char* b_lo, int K, int NR,
-                                                  int N) {
-    const uint32_t idesc = idesc_bf16(128, N, 0, 0);
-    const uint32_t a_lbo = TM * 16, b_lbo = NR * 16;
-    uint32_t acc = 0;
-    for (int ks = 0; ks < K / 16; ++ks) {
-        const uint64_t ah = smem_desc(smem_u32(a_hi) + ks * 2 * a_lbo, a_lbo, 128);
-        const uint64_t bh = smem_desc(smem_u32(b_hi) + ks * 2 * b_lbo, b_lbo, 128);
-        mma_bf16(d_tmem, ah, bh, idesc, acc);
-        acc = 1;
-        if (SPLIT == 2) {
-            const uint64_t al = smem_desc(smem_u32(a_lo) + ks * 2 * a_lbo, a_lbo, 128);
-            const uint64_t bl = smem_desc(smem_u32(b_lo) + ks * 2 * b_lbo, b_lbo, 128);
-            mma_bf16(d_tmem, ah, bl, idesc, 1);
-            mma_bf16(d_tmem, al, bh, idesc, 1);
-        }
-    }
-}
 
 // ------------------------------------------------------------------ self test of the MMA plumbing
 // mode 0: D[128][N] = A[128][K] * B[N][K]^T          (K-major operands)
@@ -158,39 +91,6 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-// ------------------------------------------------------------------ encoded-input row (tensorBase.py:43-55,116-122)
-// in tensor-core column order (see BIAS1); PE values carry the annealing masks
-// clamp(progress*2 - l, 0, 1).
-struct PEMask { float f0, f1, v0, v1; };
-
-__device__ __forceinline__ void encode_chunk(int chunk, const float feat[32], const float dir[3], const PEMask& pm,
-                                             float v[8]) {
-    if (chunk < 4) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = chunk * 8 + i;
-            v[i] = c < F_ ? feat[c] : c < F_ + 3 ? dir[c - F_] : c == BIAS1 ? 1.0f : 0.f;
-        }
-    } else if (chunk < 19) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int e = (chunk - 4) * 2 + h;
-            const bool is_view = e >= F_;
-            const float src = is_view ? dir[e - F_] : feat[e];
-            float s, co;
-            sincosf(src, &s, &co);
-            const float m0 = is_view ? pm.v0 : pm.f0, m1 = is_view ? pm.v1 : pm.f1;
-            v[4 * h + 0] = s * m0;
-            v[4 * h + 1] = (2.f * s * co) * m1;
-            v[4 * h + 2] = co * m0;
-            v[4 * h + 3] = (1.f - 2.f * s * s) * m1;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    }
 }
 
 // ------------------------------------------------------------------ fused head forward
@@ -355,13 +255,6 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
-}
-
-template <typename K>
-static int set_smem(K kernel, int bytes) {
-    if (bytes > 48 * 1024)
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return JT_ERR_LAUNCH;
-    return JT_OK;
 }
 
 }  // namespace jt

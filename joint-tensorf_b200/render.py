@@ -46,7 +46,19 @@ class RenderCfg:
         self.hidden = 64
         self.fea_prog = 1.0
         self.view_prog = 1.0
+        self.head = "fp32"          # "fp32": SIMT GEMMs (strict parity) | "tc": tcgen05 fused head
+        self.tc_fwd_split = 2       # 2: hi+lo bf16 operands (fp32-class forward), 1: plain bf16
         self.__dict__.update(kw)
+
+
+def tc_supported(cfg, afs=None, raise_if_not=False):
+    """The tensor-core head is specialised for the Blender-config head: MLP_Fea, app_dim 27,
+    hidden 64, fea_pe = view_pe = 2, 144 appearance components."""
+    ok = (cfg.shading == "MLP_Fea" and cfg.app_dim == 27 and cfg.hidden == 64 and cfg.fea_pe == 2 and
+          cfg.view_pe == 2 and (afs is None or afs.ctot == 144))
+    if not ok and raise_if_not:
+        raise _lib.JtError("head='tc' needs MLP_Fea / app_dim 27 / hidden 64 / pe 2 / 144 components; use head='fp32'")
+    return ok
 
 
 class _Head:
@@ -173,11 +185,18 @@ class VMRender(torch.autograd.Function):
 
         comps = torch.empty((cap, afs.ctot), device=dev)
         ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
-        feat = torch.empty((cap, ldf), device=dev)
-        ops.gemm_nt(comps, afs.ctot, basis_w, afs.ctot, 0, None, feat, ldf, None, 0, a_count, cap, F, afs.ctot, 0,
-                    name="basis_fwd")
         ws = {}
-        rgb = _Head.forward(cfg, ws, feat, ldf, aidx, comp.sidx, rays_d, a_count, cap, head, dev)
+        if cfg.head == "tc":
+            tc_supported(cfg, afs, raise_if_not=True)
+            feat = None
+            rgb = torch.empty((cap, 4), device=dev)
+            ops.head_fwd_tc(cfg.tc_fwd_split, comps, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w, *head, a_count, cap,
+                            cfg.fea_prog, cfg.view_prog, rgb)
+        else:
+            feat = torch.empty((cap, ldf), device=dev)
+            ops.gemm_nt(comps, afs.ctot, basis_w, afs.ctot, 0, None, feat, ldf, None, 0, a_count, cap, F, afs.ctot, 0,
+                        name="basis_fwd")
+            rgb = _Head.forward(cfg, ws, feat, ldf, aidx, comp.sidx, rays_d, a_count, cap, head, dev)
 
         rgb_pre = torch.empty((N, 3), device=dev)
         rgb_map = torch.empty((N, 3), device=dev)
@@ -234,14 +253,21 @@ class VMRender(torch.autograd.Function):
         dsamp = torch.empty((cap, 4), device=dev)
         ops.vm_gather_bwd(0, dfs, gdp, gdl, comp.samp, None, comp.count, cap, dsig, dsamp, 0)
 
-        dfeat, head_grads = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
-                                           b["a_count"], cap, b["head"], dev)
         g_basis = torch.zeros_like(b["basis_w"])
-        ops.gemm_tn(dfeat, ldf, b["comps"], afs.ctot, b["a_count"], cap, F, afs.ctot, g_basis, afs.ctot, None,
-                    name="basis_bwd_w")
         dcomps = torch.empty((cap, afs.ctot), device=dev)
-        ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
-                    afs.ctot, F, 0, name="basis_bwd_x")
+        if cfg.head == "tc":
+            w1, b1, w2, b2, w3, b3 = b["head"]
+            head_grads = [torch.zeros_like(t) for t in b["head"]]
+            ops.head_bwd_tc(b["comps"], dout, b["aidx"], comp.sidx, b["rays_d"], cfg.n_samples, cfg.ndc, b["basis_w"],
+                            w1, b1, w2, b2, w3, b["a_count"], cap, cfg.fea_prog, cfg.view_prog, dcomps,
+                            (g_basis, *head_grads))
+        else:
+            dfeat, head_grads = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
+                                               b["a_count"], cap, b["head"], dev)
+            ops.gemm_tn(dfeat, ldf, b["comps"], afs.ctot, b["a_count"], cap, F, afs.ctot, g_basis, afs.ctot, None,
+                        name="basis_bwd_w")
+            ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
+                        afs.ctot, F, 0, name="basis_bwd_x")
         ops.vm_gather_bwd(1, afs, gap, gal, comp.samp, b["aidx"], b["a_count"], cap, dcomps, dsamp, 1)
 
         d_o = torch.empty((N, 3), device=dev)

@@ -146,6 +146,10 @@ class B200_VMSplit(torch.nn.Module):
         self.kernel_density = None
         self.kernel_color = None
         self.c2f_mode = None
+        # shading-head arithmetic: "auto" = tcgen05 tensor-core head when the configuration is
+        # supported, else the fp32 SIMT head; "fp32" forces the strict-parity path; "tc" insists.
+        self.head_precision = "auto"
+        self.tc_fwd_split = 2
         self.reset(aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
                    distance_scale, rayMarch_weight_thres, fea2denseAct, near_far, step_ratio, shadingMode, pos_pe,
                    view_pe, fea_pe, featureC, volume_init_scale, volume_init_bias)
@@ -440,7 +444,11 @@ class B200_VMSplit(torch.nn.Module):
             distance_scale=float(self.distance_scale), thres=float(self.rayMarch_weight_thres),
             depth_bias=-float(self.near_far[0]) + 0.05, shading=self.shadingMode, app_dim=int(self.app_dim),
             fea_pe=int(self.fea_pe), view_pe=int(self.view_pe), hidden=int(self.featureC),
-            fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress))
+            fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress), tc_fwd_split=int(self.tc_fwd_split))
+        from .render import tc_supported
+        if self.head_precision == "tc" or (self.head_precision == "auto" and tc_supported(cfg) and
+                                           sum(self.app_n_comp) == 144):
+            cfg.head = "tc"
 
         dp, dl = self._blurred(self.density_plane, self.density_line, self.kernel_density)
         ap, al = self._blurred(self.app_plane, self.app_line, self.kernel_color)

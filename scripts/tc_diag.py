@@ -44,3 +44,35 @@ for split in (1, 2):
                   f"rgb err {float((rgb[:, :3].cpu()-ref).abs().max()):.3e}")
         except Exception:
             traceback.print_exc()
+
+print("---- backward")
+names = ["basis_mat.weight", "renderModule.mlp.0.weight", "renderModule.mlp.0.bias", "renderModule.mlp.2.weight",
+         "renderModule.mlp.2.bias", "renderModule.mlp.4.weight", "renderModule.mlp.4.bias"]
+from oracle import vm_oracle as vo
+for a_count in (128, 1000, 40000):
+    try:
+        p, comps, rays_d, sidx, aidx, S = t._head_inputs(a_count, seed=3)
+        g = torch.Generator().manual_seed(7)
+        dout = torch.randn(a_count, 3, generator=g) * 0.1
+        pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        cr = comps.clone().requires_grad_(True)
+        feat = cr @ pr["basis_mat.weight"].T
+        dirs = rays_d[(sidx[aidx.long()] // S).long()]
+        x = torch.cat([feat, dirs, vo.positional_encoding(feat, 2, 0.8), vo.positional_encoding(dirs, 2, 0.6)], -1)
+        h = torch.relu(x @ pr[names[1]].T + pr[names[2]])
+        h = torch.relu(h @ pr[names[3]].T + pr[names[4]])
+        out = h @ pr[names[5]].T + pr[names[6]]
+        (out * dout).sum().backward()
+        d = {k: v.cuda().contiguous() for k, v in p.items()}
+        dout4 = torch.zeros((a_count, 4), device="cuda"); dout4[:, :3] = dout.cuda()
+        dcomps = torch.zeros((a_count, 144), device="cuda")
+        grads = [torch.zeros_like(d[k]) for k in names]
+        cnt = torch.tensor([a_count], device="cuda", dtype=torch.int32)
+        ops.head_bwd_tc(comps.cuda(), dout4, aidx.cuda(), sidx.cuda(), rays_d.cuda(), S, False, d[names[0]],
+                        d[names[1]], d[names[2]], d[names[3]], d[names[4]], d[names[5]], cnt, a_count, 0.8, 0.6,
+                        dcomps, grads)
+        torch.cuda.synchronize()
+        rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+        print(f"bwd A={a_count}: dcomps rel {rel(dcomps, cr.grad):.3e} " + " ".join(f"{k.split('.')[-2]}.{k.split('.')[-1][0]} {rel(gk, pr[k].grad):.2e}" for k, gk in zip(names, grads)))
+    except Exception:
+        traceback.print_exc()

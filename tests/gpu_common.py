@@ -34,8 +34,9 @@ def forward_kwargs(g, device):
     return kw
 
 
-def run_module_on_golden(g, device="cuda:0"):
+def run_module_on_golden(g, device="cuda:0", head="fp32"):
     m = module_from_golden(g, device)
+    m.head_precision = head
     o = g["rays_o"].to(device).requires_grad_(True)
     d = g["rays_d"].to(device).requires_grad_(True)
     opt = default_opt(g["case"]["shading"], g["case"].get("ndc", False))

@@ -68,3 +68,37 @@ def test_head_fwd_tc_matches_fp32(split, tol, a_count):
                     d["renderModule.mlp.4.bias"], cnt, a_count + 500, 0.8, 0.6, rgb, feat)
     assert (feat[:, :27].cpu() - feat_ref).abs().max() <= tol * max(1.0, float(feat_ref.abs().max()))
     assert (rgb[:, :3].cpu() - ref).abs().max() <= tol
+
+
+@pytest.mark.parametrize("a_count", [1, 128, 1000, 40000])
+def test_head_bwd_tc_matches_fp32_autograd(a_count):
+    p, comps, rays_d, sidx, aidx, S = _head_inputs(a_count, seed=3)
+    g = torch.Generator().manual_seed(7)
+    dout = torch.randn(a_count, 3, generator=g) * 0.1
+    names = ["basis_mat.weight", "renderModule.mlp.0.weight", "renderModule.mlp.0.bias", "renderModule.mlp.2.weight",
+             "renderModule.mlp.2.bias", "renderModule.mlp.4.weight", "renderModule.mlp.4.bias"]
+    # fp32 autograd reference of the same op (pre-sigmoid output, so dout is its upstream gradient)
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    cr = comps.clone().requires_grad_(True)
+    feat = cr @ pr["basis_mat.weight"].T
+    dirs = rays_d[(sidx[aidx.long()] // S).long()]
+    x = torch.cat([feat, dirs, vo.positional_encoding(feat, 2, 0.8), vo.positional_encoding(dirs, 2, 0.6)], -1)
+    h = torch.relu(x @ pr[names[1]].T + pr[names[2]])
+    h = torch.relu(h @ pr[names[3]].T + pr[names[4]])
+    out = h @ pr[names[5]].T + pr[names[6]]
+    (out * dout).sum().backward()
+    d = {k: v.to(DEV).contiguous() for k, v in p.items()}
+    dout4 = torch.zeros((a_count, 4), device=DEV)
+    dout4[:, :3] = dout.to(DEV)
+    dcomps = torch.zeros((a_count, 144), device=DEV)
+    grads = [torch.zeros_like(d[k]) for k in names]
+    cnt = torch.tensor([a_count], device=DEV, dtype=torch.int32)
+    ops.head_bwd_tc(comps.to(DEV), dout4, aidx.to(DEV), sidx.to(DEV), rays_d.to(DEV), S, False, d[names[0]],
+                    d[names[1]], d[names[2]], d[names[3]], d[names[4]], d[names[5]], cnt, a_count + 300, 0.8, 0.6,
+                    dcomps, grads)
+    torch.cuda.synchronize()
+    def rel(a, b):
+        return float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    assert rel(dcomps, cr.grad) <= 2e-2, rel(dcomps, cr.grad)
+    for k, gk in zip(names, grads):
+        assert rel(gk, pr[k].grad) <= 2e-2, (k, rel(gk, pr[k].grad))

@@ -125,24 +125,24 @@ int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, f
  * (tensorBase.py:116-126) fused per tile of 128 appearance samples, app_dim 27 / hidden 64 /
  * fea_pe = view_pe = 2: comps [A][144] -> rgb [A][4]. split = 1: bf16 operands; split = 2:
  * every operand as hi+lo bf16 terms, 3 MMAs per product (fp32-class accuracy). feat_out
- * (optional) [A][28] receives the basis projection. */
+ * (optional) [A][28] receives the basis projection. stage (optional, training): scratch of
+ * jt_head_tc_stage_bytes(n_max) bytes, 128-byte aligned, that receives the bf16 operand tiles
+ * (components, encoded input, relu(h1), relu(h2)) jt_head_bwd_tc needs. */
+long long jt_head_tc_stage_bytes(int n_max);
 int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* sidx, const float* rays_d,
                    int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
                    const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
-                   float fea_progress, float view_progress, float* rgb, float* feat_out, cudaStream_t stream);
-
-/* Backward of jt_head_fwd_tc (bf16 tensor-core GEMMs, fp32 accumulation in TMEM): from comps
- * [A][144] and dout [A][4] (gradient at the head's pre-activation, from jt_render_bwd) computes
- * dcomps [A][144] (for jt_vm_gather_bwd) and ADDS the weight gradients into gWb [27][144],
- * gW1 [64][150], gb1, gW2 [64][64], gb2, gW3 [3][64], gb3. Activations are recomputed; `stage`
- * is scratch of jt_head_bwd_tc_stage_bytes(n_max) bytes (128-byte aligned) holding the bf16
- * operand tiles between the data-gradient and the weight-gradient kernel. */
-long long jt_head_bwd_tc_stage_bytes(int n_max);
-int jt_head_bwd_tc(const float* comps, const float* dout, const int* aidx, const int* sidx, const float* rays_d,
-                   int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
-                   const float* W2, const float* b2, const float* W3, const int* n_dev, int n_max,
-                   float fea_progress, float view_progress, float* dcomps, void* stage, float* gWb, float* gW1,
-                   float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, cudaStream_t stream);
+                   float fea_progress, float view_progress, float* rgb, float* feat_out, void* stage,
+                   cudaStream_t stream);
+/* Backward of jt_head_fwd_tc (bf16 tensor-core GEMMs, fp32 accumulation in TMEM): from dout
+ * [A][4] (gradient at the head's pre-activation, from jt_render_bwd), feat [A][28] and the
+ * tiles the forward left in `stage`, computes dcomps [A][144] (for jt_vm_gather_bwd) and ADDS
+ * the weight gradients into gWb [27][144], gW1 [64][150], gb1, gW2 [64][64], gb2, gW3 [3][64],
+ * gb3. relu masks are the forward's own; nothing is recomputed. */
+int jt_head_bwd_tc(const float* dout, const float* feat, const float* Wb, const float* W1, const float* W2,
+                   const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps, void* stage,
+                   float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                   cudaStream_t stream);
 
 /* ---- K4: alpha compositing --------------------------------------------- */
 /* feature2density (tensorBase.py:696-700; act 0 softplus, 1 relu) + raw2alpha

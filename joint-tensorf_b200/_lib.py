@@ -24,9 +24,8 @@ SIGNATURES = {
     "jt_pe_encode": [_I, _I, _I, _I, _I, _F, _F, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _P],
     "jt_sh_shade": [_I, _P, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _I, _P],
     "jt_tc_selftest": [_I, _P, _I, _P, _I, _P, _I, _I, _I, _P],
-    "jt_head_fwd_tc": [_I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],
-    "jt_head_bwd_tc": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P,
-                       _P, _P, _P],
+    "jt_head_fwd_tc": [_I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P],
+    "jt_head_bwd_tc": [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_alpha_fwd": [_P, _I, _P, _P, _P, _F, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_composite_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P],
     "jt_render_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _I, _I, _P, _P, _P, _P],
@@ -58,8 +57,8 @@ def lib():
         cdll.jt_strerror.restype = ctypes.c_char_p
         cdll.jt_version.argtypes = []
         cdll.jt_version.restype = _I
-        cdll.jt_head_bwd_tc_stage_bytes.argtypes = [_I]
-        cdll.jt_head_bwd_tc_stage_bytes.restype = ctypes.c_longlong
+        cdll.jt_head_tc_stage_bytes.argtypes = [_I]
+        cdll.jt_head_tc_stage_bytes.restype = ctypes.c_longlong
         cdll.jt_launch_count.argtypes = []
         cdll.jt_launch_count.restype = ctypes.c_longlong
         _lib = cdll

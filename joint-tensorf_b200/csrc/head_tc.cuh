@@ -121,6 +121,15 @@ __device__ __forceinline__ void encode_chunk(int chunk, const float feat[32], co
 }
 
 
+// staging block of one 128-sample tile in HBM (bytes): bf16 operand tiles in canonical layout
+constexpr int SZ_A0 = tile_bytes(TM, CT), SZ_A1 = tile_bytes(TM, K1), SZ_A2 = tile_bytes(TM, K2), SZ_A3 = SZ_A2;
+constexpr int SZ_D2 = tile_bytes(TM, H_), SZ_D1 = SZ_D2, SZ_DF = tile_bytes(TM, NB), SZ_DO = tile_bytes(TM, 8);
+constexpr int OFF_A0 = 0, OFF_A1 = OFF_A0 + SZ_A0, OFF_A2 = OFF_A1 + SZ_A1, OFF_A3 = OFF_A2 + SZ_A2;
+constexpr int OFF_D2 = OFF_A3 + SZ_A3, OFF_D1 = OFF_D2 + SZ_D2, OFF_DF = OFF_D1 + SZ_D1, OFF_DO = OFF_DF + SZ_DF;
+constexpr int STAGE_TILE_BYTES = OFF_DO + SZ_DO;        // 161792
+
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
     if (bytes > 48 * 1024)

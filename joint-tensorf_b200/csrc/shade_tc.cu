@@ -94,17 +94,24 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
 }
 
 // ------------------------------------------------------------------ fused head forward
-template <int SPLIT>
+// `stage` != nullptr (training): the bf16 (hi) operand tiles A0 comps, A1 encoded input,
+// A2 relu(h1), A3 relu(h2) of every tile are pushed to HBM with bulk async stores, in the
+// UMMA canonical layout, for the backward kernels (exact relu masks + the B operands of
+// the weight-gradient GEMMs). Two hi regions alternate so a store can drain while the
+// next operand is being built.
+template <int SPLIT, bool SAVE>
 struct FwdSmem {
     static constexpr int WB = tile_bytes(NB, CT), W1 = tile_bytes(H_, K1), W2 = tile_bytes(H_, K2);
-    static constexpr int A = tile_bytes(TM, K1);               // A0 / A1 / A2 alias one region
+    static constexpr int A = tile_bytes(TM, K1);
     static constexpr int off_wb = 0, off_w1 = off_wb + SPLIT * WB, off_w2 = off_w1 + SPLIT * W1;
-    static constexpr int off_a = off_w2 + SPLIT * W2;
-    static constexpr int off_w3 = off_a + SPLIT * A;           // fp32 [3][64] + b3[3]
+    static constexpr int off_hi0 = off_w2 + SPLIT * W2;
+    static constexpr int off_hi1 = SAVE ? off_hi0 + A : off_hi0;
+    static constexpr int off_lo = off_hi1 + A;
+    static constexpr int off_w3 = off_lo + (SPLIT == 2 ? A : 0);      // fp32 [3][64] + b3[3]
     static constexpr int total = off_w3 + (3 * H_ + 4) * 4;
 };
 
-template <int SPLIT>
+template <int SPLIT, bool SAVE>
 __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
                                                          const int* __restrict__ sidx, const float* __restrict__ rays_d,
                                                          int S, int normalize_dir, const float* __restrict__ Wb,
@@ -112,8 +119,9 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
                                                          const float* __restrict__ W2, const float* __restrict__ b2,
                                                          const float* __restrict__ W3, const float* __restrict__ b3,
                                                          const int* __restrict__ n_dev, int n_fixed, float fprog,
-                                                         float vprog, float* __restrict__ rgb, float* __restrict__ feat_out) {
-    using L = FwdSmem<SPLIT>;
+                                                         float vprog, float* __restrict__ rgb, float* __restrict__ feat_out,
+                                                         unsigned char* __restrict__ stage) {
+    using L = FwdSmem<SPLIT, SAVE>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -123,7 +131,8 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
     unsigned char* wb_hi = smem + L::off_wb;  unsigned char* wb_lo = SPLIT == 2 ? wb_hi + L::WB : nullptr;
     unsigned char* w1_hi = smem + L::off_w1;  unsigned char* w1_lo = SPLIT == 2 ? w1_hi + L::W1 : nullptr;
     unsigned char* w2_hi = smem + L::off_w2;  unsigned char* w2_lo = SPLIT == 2 ? w2_hi + L::W2 : nullptr;
-    unsigned char* a_hi = smem + L::off_a;    unsigned char* a_lo = SPLIT == 2 ? a_hi + L::A : nullptr;
+    unsigned char* hi0 = smem + L::off_hi0;   unsigned char* hi1 = smem + L::off_hi1;
+    unsigned char* lo = SPLIT == 2 ? smem + L::off_lo : nullptr;
     float* w3s = reinterpret_cast<float*>(smem + L::off_w3);
 
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -143,11 +152,14 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
     PEMask pm;
     pm.f0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f); pm.f1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
     pm.v0 = fminf(fmaxf(vprog * 2.f - 0.f, 0.f), 1.f); pm.v1 = fminf(fmaxf(vprog * 2.f - 1.f, 0.f), 1.f);
+    const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
         const int row = tile * TM + tid;
         const bool live = row < n;
-        // ---- A0: component row -> bf16
+        unsigned char* st = SAVE ? stage + (size_t)tile * STAGE_TILE_BYTES : nullptr;
+        // ---- A0: component row -> bf16 (hi0)
         {
             const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * CT);
 #pragma unroll 3
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
                 if (live) { x = __ldg(src + 2 * c); y = __ldg(src + 2 * c + 1); }
                 const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                store_chunk(a_hi, a_lo, TM, c, tid, v);
+                store_chunk(hi0, lo, TM, c, tid, v);
             }
         }
         float dir[3] = {0.f, 0.f, 0.f};
@@ -172,12 +184,18 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            issue_gemm_kmajor<SPLIT>(tmem + T_FEAT, a_hi, a_lo, wb_hi, wb_lo, CT, NB, NB);
+            issue_gemm_kmajor<SPLIT>(tmem + T_FEAT, hi0, lo, wb_hi, wb_lo, CT, NB, NB);
             mma_commit(&bar);
+            if (SAVE) {
+                bulk_s2g(st + OFF_A0, hi0, SZ_A0);
+                bulk_commit();
+                bulk_wait_read1();             // previous tile's A3 store has left hi1
+            }
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- feat -> encoded input A1
+        if (SAVE) __syncthreads();
+        // ---- feat -> encoded input A1 (hi1)
         float feat[32];
         tmem_ld32(lane_addr + T_FEAT, feat);
         if (feat_out && live) {
@@ -190,19 +208,25 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
         for (int c = 0; c < K1 / 8; ++c) {
             float v[8];
             encode_chunk(c, feat, dir, pm, v);
-            store_chunk(a_hi, a_lo, TM, c, tid, v);
+            store_chunk(hi1, lo, TM, c, tid, v);
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            issue_gemm_kmajor<SPLIT>(tmem + T_H1, a_hi, a_lo, w1_hi, w1_lo, K1, H_, H_);
+            issue_gemm_kmajor<SPLIT>(tmem + T_H1, hi1, lo, w1_hi, w1_lo, K1, H_, H_);
             mma_commit(&bar);
+            if (SAVE) {
+                bulk_s2g(st + OFF_A1, hi1, SZ_A1);
+                bulk_commit();
+                bulk_wait_read1();             // A0 store has left hi0
+            }
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- relu(h1) -> A2 (col 64 = 1 carries b2)
+        if (SAVE) __syncthreads();
+        // ---- relu(h1) -> A2 (hi0; col 64 = 1 carries b2)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float h[32];
@@ -212,26 +236,28 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(h[c * 8 + i], 0.f);
-                store_chunk(a_hi, a_lo, TM, half * 4 + c, tid, v);
+                store_chunk(hi0, lo, TM, half * 4 + c, tid, v);
             }
         }
-        {
-            const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            store_chunk(a_hi, a_lo, TM, 8, tid, one);
-            store_chunk(a_hi, a_lo, TM, 9, tid, zero);
-        }
+        store_chunk(hi0, lo, TM, 8, tid, one);
+        store_chunk(hi0, lo, TM, 9, tid, zero);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            issue_gemm_kmajor<SPLIT>(tmem + T_H2, a_hi, a_lo, w2_hi, w2_lo, K2, H_, H_);
+            issue_gemm_kmajor<SPLIT>(tmem + T_H2, hi0, lo, w2_hi, w2_lo, K2, H_, H_);
             mma_commit(&bar);
+            if (SAVE) {
+                bulk_s2g(st + OFF_A2, hi0, SZ_A2);
+                bulk_commit();
+                bulk_wait_read1();             // A1 store has left hi1
+            }
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- relu(h2) -> layer 3 + sigmoid
+        if (SAVE) __syncthreads();
+        // ---- relu(h2) -> layer 3 + sigmoid (and A3 tile into hi1 when saving)
         float o0 = w3s[3 * H_], o1 = w3s[3 * H_ + 1], o2 = w3s[3 * H_ + 2];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -239,19 +265,35 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
             tmem_ld32(lane_addr + T_H2 + 32 * half, h);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float x = fmaxf(h[i], 0.f);
-                o0 = fmaf(x, w3s[half * 32 + i], o0);
-                o1 = fmaf(x, w3s[H_ + half * 32 + i], o1);
-                o2 = fmaf(x, w3s[2 * H_ + half * 32 + i], o2);
+                h[i] = fmaxf(h[i], 0.f);
+                o0 = fmaf(h[i], w3s[half * 32 + i], o0);
+                o1 = fmaf(h[i], w3s[H_ + half * 32 + i], o1);
+                o2 = fmaf(h[i], w3s[2 * H_ + half * 32 + i], o2);
+            }
+            if (SAVE) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) store_chunk(hi1, nullptr, TM, half * 4 + c, tid, h + 8 * c);
             }
         }
         if (live)
             *reinterpret_cast<float4*>(rgb + 4 * (size_t)row) =
                 make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f);
+        if (SAVE) {
+            store_chunk(hi1, nullptr, TM, 8, tid, one);
+            store_chunk(hi1, nullptr, TM, 9, tid, zero);
+            fence_async_smem();
+        }
         // all tcgen05.ld of this tile are complete (wait::ld) before the next tile's MMAs overwrite TMEM
         tc_fence_before();
         __syncthreads();
+        if (SAVE && tid == 0) {
+            bulk_s2g(st + OFF_A3, hi1, SZ_A3);
+            bulk_commit();
+            bulk_wait_read1();                 // A2 store has left hi0 (next tile's A0 goes there)
+        }
+        if (SAVE) __syncthreads();
     }
+    if (SAVE && tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
@@ -276,26 +318,27 @@ extern "C" int jt_head_fwd_tc(int split, const float* comps, const int* aidx, co
                               int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
                               const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev,
                               int n_max, float fea_progress, float view_progress, float* rgb, float* feat_out,
-                              cudaStream_t stream) {
+                              void* stage, cudaStream_t stream) {
     JT_CHECK_ARG(comps && aidx && sidx && rays_d && Wb && W1 && b1 && W2 && b2 && W3 && b3 && rgb);
     JT_CHECK_ARG(split == 1 || split == 2);
+    JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
     if (n_max <= 0) return JT_OK;
     long long tiles = ((long long)n_max + TM - 1) / TM;
+    unsigned char* st = static_cast<unsigned char*>(stage);
     g_launches += 1;
-    if (split == 1) {
-        const int smem = FwdSmem<1>::total;
-        if (int rc = set_smem(head_fwd_tc_kernel<1>, smem)) return rc;
-        int grid = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
-        head_fwd_tc_kernel<1><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1,
-                                                          b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,
-                                                          view_progress, rgb, feat_out);
-    } else {
-        const int smem = FwdSmem<2>::total;
-        if (int rc = set_smem(head_fwd_tc_kernel<2>, smem)) return rc;
-        int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-        head_fwd_tc_kernel<2><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1,
-                                                          b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,
-                                                          view_progress, rgb, feat_out);
+#define JT_LAUNCH_FWD(SP, SV, PER_SM)                                                                                   \
+    {                                                                                                                   \
+        const int smem = FwdSmem<SP, SV>::total;                                                                        \
+        if (int rc = set_smem(head_fwd_tc_kernel<SP, SV>, smem)) return rc;                                             \
+        int grid = (int)(tiles < (PER_SM) * kNumSMs ? tiles : (PER_SM) * kNumSMs);                                      \
+        head_fwd_tc_kernel<SP, SV><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, \
+                                                               W1, b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,      \
+                                                               view_progress, rgb, feat_out, st);                       \
     }
+    if (split == 1 && !st) JT_LAUNCH_FWD(1, false, 2)
+    else if (split == 1) JT_LAUNCH_FWD(1, true, 1)
+    else if (!st) JT_LAUNCH_FWD(2, false, 1)
+    else JT_LAUNCH_FWD(2, true, 1)
+#undef JT_LAUNCH_FWD
     JT_RETURN_LAUNCH();
 }

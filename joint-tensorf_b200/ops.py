@@ -199,25 +199,27 @@ def tc_selftest(mode, a, b, k, n, ma=0):
     return d
 
 
+def head_tc_stage(n_max, device):
+    """Scratch for the bf16 operand tiles exchanged between the tensor-core head kernels."""
+    nbytes = int(_lib.lib().jt_head_tc_stage_bytes(int(n_max)))
+    return torch.empty((nbytes,), device=device, dtype=torch.uint8)
+
+
 def head_fwd_tc(split, comps, aidx, sidx, rays_d, n_samples, normalize_dir, wb, w1, b1, w2, b2, w3, b3, n_dev, n_max,
-                fprog, vprog, rgb, feat_out=None):
+                fprog, vprog, rgb, feat_out=None, stage=None):
     with TIMER.span("head_fwd_tc"):
         check(_lib.lib().jt_head_fwd_tc(split, _p(comps), _p(aidx), _p(sidx), _p(rays_d), n_samples,
                                         int(normalize_dir), _p(wb), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
                                         _p(n_dev), int(n_max), float(fprog), float(vprog), _p(rgb), _p(feat_out),
-                                        _stream()), "jt_head_fwd_tc")
+                                        _p(stage), _stream()), "jt_head_fwd_tc")
 
 
-def head_bwd_tc(comps, dout, aidx, sidx, rays_d, n_samples, normalize_dir, wb, w1, b1, w2, b2, w3, n_dev, n_max, fprog,
-                vprog, dcomps, grads):
+def head_bwd_tc(dout, feat, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, grads):
     """grads = (gWb, gW1, gb1, gW2, gb2, gW3, gb3), zero-initialised by the caller."""
-    nbytes = int(_lib.lib().jt_head_bwd_tc_stage_bytes(int(n_max)))
-    stage = torch.empty((nbytes,), device=comps.device, dtype=torch.uint8)
     with TIMER.span("head_bwd_tc"):
-        check(_lib.lib().jt_head_bwd_tc(_p(comps), _p(dout), _p(aidx), _p(sidx), _p(rays_d), n_samples,
-                                        int(normalize_dir), _p(wb), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(n_dev),
-                                        int(n_max), float(fprog), float(vprog), _p(dcomps), _p(stage),
-                                        *[_p(g) for g in grads], _stream()), "jt_head_bwd_tc")
+        check(_lib.lib().jt_head_bwd_tc(_p(dout), _p(feat), _p(wb), _p(w1), _p(w2), _p(w3), _p(n_dev), int(n_max),
+                                        float(fprog), _p(dcomps), _p(stage), *[_p(g) for g in grads], _stream()),
+              "jt_head_bwd_tc")
 
 
 # ------------------------------------------------------------------ K5

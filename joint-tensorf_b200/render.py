@@ -188,10 +188,12 @@ class VMRender(torch.autograd.Function):
         ws = {}
         if cfg.head == "tc":
             tc_supported(cfg, afs, raise_if_not=True)
-            feat = None
             rgb = torch.empty((cap, 4), device=dev)
+            train = any(ctx.needs_input_grad)
+            feat = torch.empty((cap, 28), device=dev) if train else None
+            ws["stage"] = ops.head_tc_stage(cap, dev) if train else None
             ops.head_fwd_tc(cfg.tc_fwd_split, comps, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w, *head, a_count, cap,
-                            cfg.fea_prog, cfg.view_prog, rgb)
+                            cfg.fea_prog, cfg.view_prog, rgb, feat, ws["stage"])
         else:
             feat = torch.empty((cap, ldf), device=dev)
             ops.gemm_nt(comps, afs.ctot, basis_w, afs.ctot, 0, None, feat, ldf, None, 0, a_count, cap, F, afs.ctot, 0,
@@ -258,9 +260,8 @@ class VMRender(torch.autograd.Function):
         if cfg.head == "tc":
             w1, b1, w2, b2, w3, b3 = b["head"]
             head_grads = [torch.zeros_like(t) for t in b["head"]]
-            ops.head_bwd_tc(b["comps"], dout, b["aidx"], comp.sidx, b["rays_d"], cfg.n_samples, cfg.ndc, b["basis_w"],
-                            w1, b1, w2, b2, w3, b["a_count"], cap, cfg.fea_prog, cfg.view_prog, dcomps,
-                            (g_basis, *head_grads))
+            ops.head_bwd_tc(dout, b["feat"], b["basis_w"], w1, w2, w3, b["a_count"], cap, cfg.fea_prog, dcomps,
+                            ws["stage"], (g_basis, *head_grads))
         else:
             dfeat, head_grads = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
                                                b["a_count"], cap, b["head"], dev)

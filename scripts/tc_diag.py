@@ -49,9 +49,11 @@ print("---- backward")
 names = ["basis_mat.weight", "renderModule.mlp.0.weight", "renderModule.mlp.0.bias", "renderModule.mlp.2.weight",
          "renderModule.mlp.2.bias", "renderModule.mlp.4.weight", "renderModule.mlp.4.bias"]
 from oracle import vm_oracle as vo
-for a_count in (128, 1000, 40000):
+for a_count, bias in ((128, 0.0), (1000, 0.0), (40000, 0.0), (1000, 3.0), (40000, 3.0)):
     try:
         p, comps, rays_d, sidx, aidx, S = t._head_inputs(a_count, seed=3)
+        p["renderModule.mlp.0.bias"] += bias      # bias 3.0: every unit active -> no relu-mask flips between precisions
+        p["renderModule.mlp.2.bias"] += bias
         g = torch.Generator().manual_seed(7)
         dout = torch.randn(a_count, 3, generator=g) * 0.1
         pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
@@ -68,11 +70,16 @@ for a_count in (128, 1000, 40000):
         dcomps = torch.zeros((a_count, 144), device="cuda")
         grads = [torch.zeros_like(d[k]) for k in names]
         cnt = torch.tensor([a_count], device="cuda", dtype=torch.int32)
-        ops.head_bwd_tc(comps.cuda(), dout4, aidx.cuda(), sidx.cuda(), rays_d.cuda(), S, False, d[names[0]],
-                        d[names[1]], d[names[2]], d[names[3]], d[names[4]], d[names[5]], cnt, a_count, 0.8, 0.6,
-                        dcomps, grads)
+        rgb = torch.zeros((a_count, 4), device="cuda"); feat_d = torch.zeros((a_count, 28), device="cuda")
+        stage = ops.head_tc_stage(a_count, "cuda")
+        ops.head_fwd_tc(2, comps.cuda(), aidx.cuda(), sidx.cuda(), rays_d.cuda(), S, False, *[d[k] for k in names],
+                        cnt, a_count, 0.8, 0.6, rgb, feat_d, stage)
+        ref_rgb = torch.sigmoid(out.detach())
+        print(f"   fwd(save) rgb err {float((rgb[:, :3].cpu() - ref_rgb).abs().max()):.3e}")
+        ops.head_bwd_tc(dout4, feat_d, d[names[0]], d[names[1]], d[names[3]], d[names[5]], cnt, a_count, 0.8,
+                        dcomps, stage, grads)
         torch.cuda.synchronize()
         rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
-        print(f"bwd A={a_count}: dcomps rel {rel(dcomps, cr.grad):.3e} " + " ".join(f"{k.split('.')[-2]}.{k.split('.')[-1][0]} {rel(gk, pr[k].grad):.2e}" for k, gk in zip(names, grads)))
+        print(f"bwd A={a_count} bias+{bias}: dcomps rel {rel(dcomps, cr.grad):.3e} " + " ".join(f"{k.split('.')[-2]}.{k.split('.')[-1][0]} {rel(gk, pr[k].grad):.2e}" for k, gk in zip(names, grads)))
     except Exception:
         traceback.print_exc()

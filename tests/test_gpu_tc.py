@@ -93,9 +93,13 @@ def test_head_bwd_tc_matches_fp32_autograd(a_count):
     dcomps = torch.zeros((a_count, 144), device=DEV)
     grads = [torch.zeros_like(d[k]) for k in names]
     cnt = torch.tensor([a_count], device=DEV, dtype=torch.int32)
-    ops.head_bwd_tc(comps.to(DEV), dout4, aidx.to(DEV), sidx.to(DEV), rays_d.to(DEV), S, False, d[names[0]],
-                    d[names[1]], d[names[2]], d[names[3]], d[names[4]], d[names[5]], cnt, a_count + 300, 0.8, 0.6,
-                    dcomps, grads)
+    rgb = torch.zeros((a_count, 4), device=DEV)
+    feat_d = torch.zeros((a_count, 28), device=DEV)
+    stage = ops.head_tc_stage(a_count + 300, DEV)
+    ops.head_fwd_tc(2, comps.to(DEV), aidx.to(DEV), sidx.to(DEV), rays_d.to(DEV), S, False, *[d[k] for k in names],
+                    cnt, a_count + 300, 0.8, 0.6, rgb, feat_d, stage)
+    ops.head_bwd_tc(dout4, feat_d, d[names[0]], d[names[1]], d[names[3]], d[names[5]], cnt, a_count + 300, 0.8,
+                    dcomps, stage, grads)
     torch.cuda.synchronize()
     def rel(a, b):
         return float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--head", default="auto", choices=["auto", "tc", "fp32"],
+                    help="shading head: tcgen05 tensor-core kernels (auto/tc) or strict-fp32 SIMT GEMMs")
     return ap.parse_args()
 
 
@@ -181,6 +183,9 @@ def gemm_flops(name, A, F, ctot, in_dim, H):
         "mlp_l1_fwd": 2 * A * in_dim * H, "mlp_l1_bwd_x": 2 * A * in_dim * H, "mlp_l1_bwd_w": 2 * A * in_dim * H,
         "mlp_l2_fwd": 2 * A * H * H, "mlp_l2_bwd_x": 2 * A * H * H, "mlp_l2_bwd_w": 2 * A * H * H,
         "mlp_l3_fwd": 2 * A * H * 3, "mlp_l3_bwd_x": 2 * A * H * 3, "mlp_l3_bwd_w": 2 * A * H * 3,
+        # fused tensor-core head: basis + 3 layers forward; data + weight gradients backward
+        "head_fwd_tc": 2 * A * (F * ctot + in_dim * H + H * H + H * 3),
+        "head_bwd_tc": 4 * A * (F * ctot + in_dim * H + H * H + H * 3),
     }
     return table.get(name)
 
@@ -212,6 +217,7 @@ def own_arm(args):
     torch.manual_seed(0)                       # identical replicas on every rank
     model = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), dev, **kw)
     from joint_tensorf_b200.options import default_opt
+    model.head_precision = args.head
     opt = default_opt(model.shadingMode, run["ndc"])
     N, S = args.rays, run["n_samples"]
     o_h, d_h, _ = jt.synth.blender_rays(N, 32, seed=1 + rank)
@@ -338,9 +344,12 @@ def own_arm(args):
         line = {
             "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.head == "fp32" else "f32 (VM gather/scatter, compositing, blur) + bf16 tensor-core "
+                     "shading head (forward: split hi+lo operands = fp32-class; backward: bf16 operands, fp32 accumulate)",
+            "data": "synthetic",
             "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, "
-                                   f"S={S}, {N} rays/GPU, fwd+bwd, optimizer step excluded",
+                                   f"S={S}, {N} rays/GPU, fwd+bwd, optimizer step excluded", "head": args.head,
                        "blur": args.blur, "l2": "256 MB write between timed steps (L2 flushed)",
                        "parallelism": f"ray-sharded x{world}, NCCL all-reduce of a flat fp32 gradient bucket"},
             "e2e": {"value": rays_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -111,8 +111,14 @@ struct FwdSmem {
     static constexpr int total = off_w3 + (3 * H_ + 4) * 4;
 };
 
+// Two threads share a sample row: thread (r, hh) with r = tid & 127 (= TMEM lane) and
+// hh = tid >> 7 owns one half of the columns of every operand tile, so the per-row
+// instruction chains are half as long and each SM sub-partition has two warps to switch
+// between while one waits on memory / TMEM.
+constexpr int NT = 2 * TM;
+
 template <int SPLIT, bool SAVE>
-__global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
+__global__ void __launch_bounds__(NT) head_fwd_tc_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
                                                          const int* __restrict__ sidx, const float* __restrict__ rays_d,
                                                          int S, int normalize_dir, const float* __restrict__ Wb,
                                                          const float* __restrict__ W1, const float* __restrict__ b1,
@@ -125,7 +131,9 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ float part[TM][3];                 // layer-3 partial sums of the hh = 1 half
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TM - 1), hh = tid >> 7;
     const int n = n_dev ? *n_dev : n_fixed;
 
     unsigned char* wb_hi = smem + L::off_wb;  unsigned char* wb_lo = SPLIT == 2 ? wb_hi + L::WB : nullptr;
@@ -140,34 +148,32 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
     stage_weight(wb_hi, wb_lo, Wb, CT, F_, CT, NB, CT, nullptr, -1, 0);
     stage_weight(w1_hi, w1_lo, W1, IN_, H_, IN_, H_, K1, b1, BIAS1, 1);
     stage_weight(w2_hi, w2_lo, W2, H_, H_, H_, H_, K2, b2, H_, 0);
-    for (int i = tid; i < 3 * H_ + 3; i += TM) w3s[i] = i < 3 * H_ ? W3[i] : b3[i - 3 * H_];
+    for (int i = tid; i < 3 * H_ + 3; i += NT) w3s[i] = i < 3 * H_ ? W3[i] : b3[i - 3 * H_];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t T_FEAT = 0, T_H1 = 32, T_H2 = 96;
     uint32_t phase = 0;
     PEMask pm;
     pm.f0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f); pm.f1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
     pm.v0 = fminf(fmaxf(vprog * 2.f - 0.f, 0.f), 1.f); pm.v1 = fminf(fmaxf(vprog * 2.f - 1.f, 0.f), 1.f);
-    const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
-        const int row = tile * TM + tid;
+        const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = SAVE ? stage + (size_t)tile * STAGE_TILE_BYTES : nullptr;
-        // ---- A0: component row -> bf16 (hi0)
+        // ---- A0: component row -> bf16 (hi0); this thread converts chunks [9 hh, 9 hh + 9)
         {
-            const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * CT);
+            const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * CT) + 18 * hh;
 #pragma unroll 3
-            for (int c = 0; c < CT / 8; ++c) {
+            for (int c = 0; c < CT / 16; ++c) {
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-                if (live) { x = __ldg(src + 2 * c); y = __ldg(src + 2 * c + 1); }
+                if (live) { x = __ldcs(src + 2 * c); y = __ldcs(src + 2 * c + 1); }
                 const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                store_chunk(hi0, lo, TM, c, tid, v);
+                store_chunk(hi0, lo, TM, 9 * hh + c, r, v);
             }
         }
         float dir[3] = {0.f, 0.f, 0.f};
@@ -195,20 +201,29 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         if (SAVE) __syncthreads();
-        // ---- feat -> encoded input A1 (hi1)
+        // ---- feat -> encoded input A1 (hi1); chunks [10 hh, 10 hh + 10)
         float feat[32];
         tmem_ld32(lane_addr + T_FEAT, feat);
-        if (feat_out && live) {
+        if (feat_out && live && hh == 0) {
 #pragma unroll
             for (int q = 0; q < 7; ++q)
                 *reinterpret_cast<float4*>(feat_out + (size_t)row * 28 + 4 * q) =
                     make_float4(feat[4 * q], feat[4 * q + 1], feat[4 * q + 2], q == 6 ? 0.f : feat[4 * q + 3]);
         }
+        if (hh == 0) {
 #pragma unroll
-        for (int c = 0; c < K1 / 8; ++c) {
-            float v[8];
-            encode_chunk(c, feat, dir, pm, v);
-            store_chunk(hi1, lo, TM, c, tid, v);
+            for (int c = 0; c < K1 / 16; ++c) {
+                float v[8];
+                encode_chunk(c, feat, dir, pm, v);
+                store_chunk(hi1, lo, TM, c, r, v);
+            }
+        } else {
+#pragma unroll
+            for (int c = K1 / 16; c < K1 / 8; ++c) {
+                float v[8];
+                encode_chunk(c, feat, dir, pm, v);
+                store_chunk(hi1, lo, TM, c, r, v);
+            }
         }
         fence_async_smem();
         tc_fence_before();
@@ -226,21 +241,20 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         if (SAVE) __syncthreads();
-        // ---- relu(h1) -> A2 (hi0; col 64 = 1 carries b2)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        // ---- relu(h1) -> A2 (hi0; col 64 = 1 carries b2); columns [32 hh, 32 hh + 32)
+        {
             float h[32];
-            tmem_ld32(lane_addr + T_H1 + 32 * half, h);
+            tmem_ld32(lane_addr + T_H1 + 32 * hh, h);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(h[c * 8 + i], 0.f);
-                store_chunk(hi0, lo, TM, half * 4 + c, tid, v);
+                store_chunk(hi0, lo, TM, hh * 4 + c, r, v);
             }
+            const float pad[8] = {hh == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_chunk(hi0, lo, TM, 8 + hh, r, pad);
         }
-        store_chunk(hi0, lo, TM, 8, tid, one);
-        store_chunk(hi0, lo, TM, 9, tid, zero);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -257,41 +271,41 @@ __global__ void __launch_bounds__(TM) head_fwd_tc_kernel(const float* __restrict
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         if (SAVE) __syncthreads();
-        // ---- relu(h2) -> layer 3 + sigmoid (and A3 tile into hi1 when saving)
-        float o0 = w3s[3 * H_], o1 = w3s[3 * H_ + 1], o2 = w3s[3 * H_ + 2];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        // ---- relu(h2) -> layer 3 partial sums (and A3 tile into hi1 when saving)
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        {
             float h[32];
-            tmem_ld32(lane_addr + T_H2 + 32 * half, h);
+            tmem_ld32(lane_addr + T_H2 + 32 * hh, h);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 h[i] = fmaxf(h[i], 0.f);
-                o0 = fmaf(h[i], w3s[half * 32 + i], o0);
-                o1 = fmaf(h[i], w3s[H_ + half * 32 + i], o1);
-                o2 = fmaf(h[i], w3s[2 * H_ + half * 32 + i], o2);
+                o0 = fmaf(h[i], w3s[hh * 32 + i], o0);
+                o1 = fmaf(h[i], w3s[H_ + hh * 32 + i], o1);
+                o2 = fmaf(h[i], w3s[2 * H_ + hh * 32 + i], o2);
             }
             if (SAVE) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_chunk(hi1, nullptr, TM, half * 4 + c, tid, h + 8 * c);
+                for (int c = 0; c < 4; ++c) store_chunk(hi1, nullptr, TM, hh * 4 + c, r, h + 8 * c);
+                const float pad[8] = {hh == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                store_chunk(hi1, nullptr, TM, 8 + hh, r, pad);
+                fence_async_smem();
             }
         }
-        if (live)
-            *reinterpret_cast<float4*>(rgb + 4 * (size_t)row) =
-                make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f);
-        if (SAVE) {
-            store_chunk(hi1, nullptr, TM, 8, tid, one);
-            store_chunk(hi1, nullptr, TM, 9, tid, zero);
-            fence_async_smem();
-        }
+        if (hh == 1) { part[r][0] = o0; part[r][1] = o1; part[r][2] = o2; }
         // all tcgen05.ld of this tile are complete (wait::ld) before the next tile's MMAs overwrite TMEM
         tc_fence_before();
         __syncthreads();
+        if (hh == 0 && live) {
+            o0 += part[r][0] + w3s[3 * H_]; o1 += part[r][1] + w3s[3 * H_ + 1]; o2 += part[r][2] + w3s[3 * H_ + 2];
+            __stcs(reinterpret_cast<float4*>(rgb + 4 * (size_t)row),
+                   make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f));
+        }
         if (SAVE && tid == 0) {
             bulk_s2g(st + OFF_A3, hi1, SZ_A3);
             bulk_commit();
             bulk_wait_read1();                 // A2 store has left hi0 (next tile's A0 goes there)
         }
-        if (SAVE) __syncthreads();
+        __syncthreads();                       // `part` and hi0 are free for the next tile
     }
     if (SAVE && tid == 0) bulk_wait0();
     tc_fence_before();
@@ -331,7 +345,7 @@ extern "C" int jt_head_fwd_tc(int split, const float* comps, const int* aidx, co
         const int smem = FwdSmem<SP, SV>::total;                                                                        \
         if (int rc = set_smem(head_fwd_tc_kernel<SP, SV>, smem)) return rc;                                             \
         int grid = (int)(tiles < (PER_SM) * kNumSMs ? tiles : (PER_SM) * kNumSMs);                                      \
-        head_fwd_tc_kernel<SP, SV><<<grid, TM, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, \
+        head_fwd_tc_kernel<SP, SV><<<grid, NT, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, \
                                                                W1, b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,      \
                                                                view_progress, rgb, feat_out, st);                       \
     }

@@ -51,7 +51,9 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint4 q) {
     return m;
 }
 
-__global__ void __launch_bounds__(TM) head_bwd_data_kernel(
+constexpr int NTB = 2 * TM;     // two threads per sample row (column halves), as in the forward kernel
+
+__global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
     const float* __restrict__ dout, const float* __restrict__ feat_in, const float* __restrict__ Wb,
     const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
     const int* __restrict__ n_dev, int n_fixed, float fprog, float* __restrict__ dcomps,
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(TM) head_bwd_data_kernel(
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TM - 1), hh = tid >> 7;
     const int n = n_dev ? *n_dev : n_fixed;
 
     unsigned char* w2t = smem + L::off_w2t; unsigned char* w1t = smem + L::off_w1t; unsigned char* wbt = smem + L::off_wbt;
@@ -71,43 +74,44 @@ __global__ void __launch_bounds__(TM) head_bwd_data_kernel(
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     stage_tile(w2t, nullptr, H_, H_, [&](int i, int j) { return W2[(size_t)j * H_ + i]; });             // B(n=i,k=j)
-    stage_tile(w1t, nullptr, K1, H_, [&](int c, int j) { const int r = ref_col_l1(c); return r >= 0 ? W1[(size_t)j * IN_ + r] : 0.f; });
+    stage_tile(w1t, nullptr, K1, H_, [&](int c, int j) { const int rc = ref_col_l1(c); return rc >= 0 ? W1[(size_t)j * IN_ + rc] : 0.f; });
     stage_tile(wbt, nullptr, CT, NB, [&](int ic, int m) { return m < F_ ? Wb[(size_t)m * CT + ic] : 0.f; });
-    for (int i = tid; i < 3 * H_; i += TM) w3s[i] = W3[i];
+    for (int i = tid; i < 3 * H_; i += NTB) w3s[i] = W3[i];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t T_DH1 = 0, T_DIN = 64, T_DC = 0;
     uint32_t phase = 0;
     const float pf0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f), pf1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
 
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
-        const int row = tile * TM + tid;
+        const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = stage + (size_t)tile * STAGE_TILE_BYTES;
-        // ---- S0: dh2 = (dout W3) . [h2 > 0] -> D2 ; dout -> DO
+        // ---- S0: dh2 = (dout W3) . [h2 > 0] -> D2 (this thread: columns [32 hh, 32 hh + 32)) ; dout -> DO
         float go[3] = {0.f, 0.f, 0.f};
         if (live) {
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(dout) + row);
             go[0] = g4.x; go[1] = g4.y; go[2] = g4.z;
         }
-        {
+        if (hh == 0) {
             const float v[8] = {go[0], go[1], go[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-            store_chunk(DO, nullptr, TM, 0, tid, v);
+            store_chunk(DO, nullptr, TM, 0, r, v);
         }
 #pragma unroll
-        for (int c = 0; c < H_ / 8; ++c) {
-            const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + (size_t)c * TM * 16 + tid * 16)));
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = hh * 4 + c4;
+            const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + (size_t)c * TM * 16 + r * 16)));
             float g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int j = c * 8 + i;
                 g[i] = ((m >> i) & 1u) ? go[0] * w3s[j] + go[1] * w3s[H_ + j] + go[2] * w3s[2 * H_ + j] : 0.f;
             }
-            store_chunk(D2, nullptr, TM, c, tid, g);
+            store_chunk(D2, nullptr, TM, c, r, g);
         }
         fence_async_smem();
         tc_fence_before();
@@ -123,18 +127,17 @@ __global__ void __launch_bounds__(TM) head_bwd_data_kernel(
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
         // ---- S1: dh1 = dh1_pre . [h1 > 0] -> D1
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
             float g[32];
-            tmem_ld32(lane_addr + T_DH1 + 32 * half, g);
+            tmem_ld32(lane_addr + T_DH1 + 32 * hh, g);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int cc = half * 4 + c;
-                const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + (size_t)cc * TM * 16 + tid * 16)));
+                const int cc = hh * 4 + c;
+                const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + (size_t)cc * TM * 16 + r * 16)));
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? g[c * 8 + i] : 0.f;
-                store_chunk(D1, nullptr, TM, cc, tid, v);
+                store_chunk(D1, nullptr, TM, cc, r, v);
             }
         }
         fence_async_smem();
@@ -149,40 +152,40 @@ __global__ void __launch_bounds__(TM) head_bwd_data_kernel(
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- S2: din -> dfeat (chain rule through the encoding) -> DF
-        float df[32];
+        // ---- S2: din -> dfeat (chain rule through the encoding) -> DF; this thread: elements [16 hh, 16 hh + 16)
         {
-            float g[32];
-            tmem_ld32(lane_addr + T_DIN, g);
+            float df[16], raw[32];
+            tmem_ld32(lane_addr + T_DIN, raw);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) df[e] = e < F_ ? g[e] : 0.f;
-        }
-        float feat[28];
-        {
-            const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * 28);
+            for (int e = 0; e < 16; ++e) df[e] = (16 * hh + e < F_) ? (hh == 0 ? raw[e] : raw[16 + e]) : 0.f;
+            float feat[16];
+            {
+                const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * 28) + 4 * hh;
 #pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                const float4 f4 = live ? __ldg(fp + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                      // 8 source elements per 32 columns
-            float g[32];
-            tmem_ld32(lane_addr + T_DIN + 32 * (k + 1), g);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int e = 8 * k + q;
-                if (e < F_) {
-                    float s, co;
-                    sincosf(feat[e], &s, &co);
-                    const float s2 = 2.f * s * co, c2 = 1.f - 2.f * s * s;
-                    df[e] += pf0 * (co * g[4 * q] - s * g[4 * q + 2]) + 2.f * pf1 * (c2 * g[4 * q + 1] - s2 * g[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) {
+                    float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && (hh == 0 || q < 3)) f4 = __ldg(fp + q);
+                    feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
                 }
             }
-        }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) store_chunk(DF, nullptr, TM, c, tid, df + 8 * c);
+            for (int k = 0; k < 2; ++k) {                      // 8 source elements per 32 columns
+                float g[32];
+                tmem_ld32(lane_addr + T_DIN + 32 + 64 * hh + 32 * k, g);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int el = 8 * k + q;
+                    if (16 * hh + el < F_) {
+                        float sn, co;
+                        sincosf(feat[el], &sn, &co);
+                        const float s2 = 2.f * sn * co, c2 = 1.f - 2.f * sn * sn;
+                        df[el] += pf0 * (co * g[4 * q] - sn * g[4 * q + 2]) + 2.f * pf1 * (c2 * g[4 * q + 1] - s2 * g[4 * q + 3]);
+                    }
+                }
+            }
+            store_chunk(DF, nullptr, TM, 2 * hh, r, df);
+            store_chunk(DF, nullptr, TM, 2 * hh + 1, r, df + 8);
+        }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -195,23 +198,26 @@ __global__ void __launch_bounds__(TM) head_bwd_data_kernel(
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- S3: dcomps row -> global (fp32)
+        // ---- S3: dcomps row -> global (fp32); hh = 0: columns [0,64) + [128,144), hh = 1: [64,128)
         {
             float4* dst = reinterpret_cast<float4*>(dcomps + (size_t)(live ? row : 0) * CT);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 float g[32];
-                tmem_ld32(lane_addr + T_DC + 32 * k, g);
+                const int c0 = 64 * hh + 32 * k;
+                tmem_ld32(lane_addr + T_DC + c0, g);
                 if (live) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) dst[8 * k + q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                    for (int q = 0; q < 8; ++q) __stcs(dst + c0 / 4 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
                 }
             }
-            float g[16];
-            tmem_ld16(lane_addr + T_DC + 128, g);
-            if (live) {
+            if (hh == 0) {
+                float g[16];
+                tmem_ld16(lane_addr + T_DC + 128, g);
+                if (live) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) dst[32 + q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q) __stcs(dst + 32 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+                }
             }
         }
         if (tid == 0) bulk_wait_read0();       // D2 / D1 / DF / DO have left shared memory
@@ -358,7 +364,7 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, const float*
     if (int rc = set_smem(head_bwd_data_kernel, BwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_wgrad_kernel, WG_STAGES * WG_STAGE_BYTES)) return rc;
     g_launches += 2;
-    head_bwd_data_kernel<<<grid_d, TM, BwdSmem::total, stream>>>(dout, feat, Wb, W1, W2, W3, n_dev, n_max, fea_progress,
+    head_bwd_data_kernel<<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, Wb, W1, W2, W3, n_dev, n_max, fea_progress,
                                                                  dcomps, static_cast<unsigned char*>(stage));
     head_bwd_wgrad_kernel<<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(static_cast<const unsigned char*>(stage),
                                                                               n_dev, n_max, gWb, gW1, gb1, gW2, gb2,

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) vm_fwd_kernel(Factors F, const float4* __
                     float4 pv = f4_bilin(a, t.w00, b, t.w10, c, t.w01, d, t.w11);
                     float4 lv = f4_lerp2(la, t.tl.w0, lb, t.tl.w1);
                     if (APP) {
-                        *reinterpret_cast<float4*>(out + (size_t)e * F.ctot + F.off[i] + q) = f4_mul(pv, lv);
+                        __stcs(reinterpret_cast<float4*>(out + (size_t)e * F.ctot + F.off[i] + q), f4_mul(pv, lv));
                     } else {
                         acc += f4_dot(pv, lv);
                     }
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) vm_bwd_kernel(Factors F, FactorGrads G, c
                 for (int q = sub * 4; q < C; q += 16) {
                     float4 a = ldg4(t.p00 + q), b = ldg4(t.p10 + q), c = ldg4(t.p01 + q), d = ldg4(t.p11 + q);
                     float4 la = ldg4(t.l0 + q), lb = ldg4(t.l1 + q);
-                    float4 g4 = APP ? ldg4(gin + (size_t)e * F.ctot + F.off[i] + q) : make_float4(gs, gs, gs, gs);
+                    float4 g4 = APP ? __ldcs(reinterpret_cast<const float4*>(gin + (size_t)e * F.ctot + F.off[i] + q)) : make_float4(gs, gs, gs, gs);
                     float4 pv = f4_bilin(a, t.w00, b, t.w10, c, t.w01, d, t.w11);
                     float4 lv = f4_lerp2(la, t.tl.w0, lb, t.tl.w1);
                     float4 gl = f4_mul(g4, lv);      // dL/dP (interpolated)

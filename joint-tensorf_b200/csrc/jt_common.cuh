@@ -66,8 +66,10 @@ __device__ __forceinline__ float quad_sum(float v) {       // over the 4 lanes s
 
 // Vector reduction into global memory: one 16-byte RED per call (sm_90+).
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    // no "memory" clobber on purpose: the gradient buffers are never read by the issuing kernel, and a
+    // clobber would pin every later tap load behind the reduction (it serialised the scatter kernels)
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
-                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

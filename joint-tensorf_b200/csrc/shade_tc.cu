@@ -161,30 +161,42 @@ __global__ void __launch_bounds__(NT) head_fwd_tc_kernel(const float* __restrict
     pm.f0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f); pm.f1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
     pm.v0 = fminf(fmaxf(vprog * 2.f - 0.f, 0.f), 1.f); pm.v1 = fminf(fmaxf(vprog * 2.f - 1.f, 0.f), 1.f);
 
+    // software prefetch: the 72 KB component tile (and the view direction) of the NEXT tile is
+    // loaded into registers while the current tile runs its three GEMM phases, so the DRAM
+    // latency of the only large global read of this kernel is off the critical path.
+    float4 nx[CT / 8];                           // this thread's half row: 18 float4
+    float pd[3];
+    auto prefetch = [&](int t) {
+        const long long rw = (long long)t * TM + r;
+        const bool lv = rw < n;
+        const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(lv ? rw : 0) * CT) + 18 * hh;
+#pragma unroll
+        for (int c = 0; c < CT / 8; ++c) nx[c] = lv ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pd[0] = pd[1] = pd[2] = 0.f;
+        if (lv) {
+            const int ray = sidx[aidx[rw]] / S;
+            pd[0] = rays_d[3 * ray]; pd[1] = rays_d[3 * ray + 1]; pd[2] = rays_d[3 * ray + 2];
+        }
+    };
+    prefetch(blockIdx.x);
+
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
         const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = SAVE ? stage + (size_t)tile * STAGE_TILE_BYTES : nullptr;
         // ---- A0: component row -> bf16 (hi0); this thread converts chunks [9 hh, 9 hh + 9)
-        {
-            const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * CT) + 18 * hh;
-#pragma unroll 3
-            for (int c = 0; c < CT / 16; ++c) {
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-                if (live) { x = __ldcs(src + 2 * c); y = __ldcs(src + 2 * c + 1); }
-                const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-                store_chunk(hi0, lo, TM, 9 * hh + c, r, v);
-            }
+#pragma unroll
+        for (int c = 0; c < CT / 16; ++c) {
+            const float4 x = nx[2 * c], y = nx[2 * c + 1];
+            const float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            store_chunk(hi0, lo, TM, 9 * hh + c, r, v);
         }
-        float dir[3] = {0.f, 0.f, 0.f};
-        if (live) {
-            const int ray = sidx[aidx[row]] / S;
-            dir[0] = rays_d[3 * ray]; dir[1] = rays_d[3 * ray + 1]; dir[2] = rays_d[3 * ray + 2];
-            if (normalize_dir) {
-                const float nn = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-                dir[0] /= nn; dir[1] /= nn; dir[2] /= nn;
-            }
+        float dir[3] = {pd[0], pd[1], pd[2]};
+        if (normalize_dir && live) {
+            const float nn = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+            dir[0] /= nn; dir[1] /= nn; dir[2] /= nn;
         }
+        prefetch(tile + gridDim.x);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();

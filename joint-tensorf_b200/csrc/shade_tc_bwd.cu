@@ -91,12 +91,30 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
         const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = stage + (size_t)tile * STAGE_TILE_BYTES;
-        // ---- S0: dh2 = (dout W3) . [h2 > 0] -> D2 (this thread: columns [32 hh, 32 hh + 32)) ; dout -> DO
+        // ---- all global reads of the tile are issued up front (independent loads in flight together)
         float go[3] = {0.f, 0.f, 0.f};
-        if (live) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dout) + row);
-            go[0] = g4.x; go[1] = g4.y; go[2] = g4.z;
+        uint4 q3[4], q2[4];
+        float feat[16];
+        {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const size_t o = (size_t)(hh * 4 + c4) * TM * 16 + r * 16;
+                q3[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + o));
+                q2[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + o));
+            }
+            const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * 28) + 4 * hh;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && (hh == 0 || q < 3)) f4 = __ldg(fp + q);
+                feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
+            }
+            if (live) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(dout) + row);
+                go[0] = g4.x; go[1] = g4.y; go[2] = g4.z;
+            }
         }
+        // ---- S0: dh2 = (dout W3) . [h2 > 0] -> D2 (this thread: columns [32 hh, 32 hh + 32)) ; dout -> DO
         if (hh == 0) {
             const float v[8] = {go[0], go[1], go[2], 0.f, 0.f, 0.f, 0.f, 0.f};
             store_chunk(DO, nullptr, TM, 0, r, v);
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const int c = hh * 4 + c4;
-            const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + (size_t)c * TM * 16 + r * 16)));
+            const uint32_t m = chunk_mask(q3[c4]);
             float g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int cc = hh * 4 + c;
-                const uint32_t m = chunk_mask(__ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + (size_t)cc * TM * 16 + r * 16)));
+                const uint32_t m = chunk_mask(q2[c]);
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = ((m >> i) & 1u) ? g[c * 8 + i] : 0.f;
@@ -158,16 +176,6 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
             tmem_ld32(lane_addr + T_DIN, raw);
 #pragma unroll
             for (int e = 0; e < 16; ++e) df[e] = (16 * hh + e < F_) ? (hh == 0 ? raw[e] : raw[16 + e]) : 0.f;
-            float feat[16];
-            {
-                const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * 28) + 4 * hh;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live && (hh == 0 || q < 3)) f4 = __ldg(fp + q);
-                    feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
-                }
-            }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {                      // 8 source elements per 32 columns
                 float g[32];

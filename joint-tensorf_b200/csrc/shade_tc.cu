@@ -16,6 +16,7 @@
 // SPLIT = 2 stores every operand as hi + lo bf16 terms and issues 3 MMAs
 // (hi*hi + hi*lo + lo*hi): ~2^-16 relative product error, i.e. fp32-class results
 // from bf16 tensor-core throughput. SPLIT = 1 is plain bf16.
+#include <stdlib.h>
 #include "head_tc.cuh"
 #include "../../include/jt_vm.h"
 
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(NT) head_fwd_tc_kernel(const float* __restrict
                                                          const float* __restrict__ W3, const float* __restrict__ b3,
                                                          const int* __restrict__ n_dev, int n_fixed, float fprog,
                                                          float vprog, float* __restrict__ rgb, float* __restrict__ feat_out,
-                                                         unsigned char* __restrict__ stage) {
+                                                         unsigned char* __restrict__ stage, int ahead) {
     using L = FwdSmem<SPLIT, SAVE>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -178,13 +179,14 @@ __global__ void __launch_bounds__(NT) head_fwd_tc_kernel(const float* __restrict
             pd[0] = rays_d[3 * ray]; pd[1] = rays_d[3 * ray + 1]; pd[2] = rays_d[3 * ray + 2];
         }
     };
-    prefetch(blockIdx.x);
+    if (ahead) prefetch(blockIdx.x);
 
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
         const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = SAVE ? stage + (size_t)tile * STAGE_TILE_BYTES : nullptr;
         // ---- A0: component row -> bf16 (hi0); this thread converts chunks [9 hh, 9 hh + 9)
+        if (!ahead) prefetch(tile);
 #pragma unroll
         for (int c = 0; c < CT / 16; ++c) {
             const float4 x = nx[2 * c], y = nx[2 * c + 1];
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NT) head_fwd_tc_kernel(const float* __restrict
             const float nn = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
             dir[0] /= nn; dir[1] /= nn; dir[2] /= nn;
         }
-        prefetch(tile + gridDim.x);
+        if (ahead) prefetch(tile + gridDim.x);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -351,6 +353,8 @@ extern "C" int jt_head_fwd_tc(int split, const float* comps, const int* aidx, co
     if (n_max <= 0) return JT_OK;
     long long tiles = ((long long)n_max + TM - 1) / TM;
     unsigned char* st = static_cast<unsigned char*>(stage);
+    static const char* env_pf = getenv("JT_TC_PREFETCH");      // tuning: 0 loads the component tile in place
+    const int ahead = env_pf ? atoi(env_pf) : 1;
     g_launches += 1;
 #define JT_LAUNCH_FWD(SP, SV, PER_SM)                                                                                   \
     {                                                                                                                   \
@@ -359,7 +363,7 @@ extern "C" int jt_head_fwd_tc(int split, const float* comps, const int* aidx, co
         int grid = (int)(tiles < (PER_SM) * kNumSMs ? tiles : (PER_SM) * kNumSMs);                                      \
         head_fwd_tc_kernel<SP, SV><<<grid, NT, smem, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, \
                                                                W1, b1, W2, b2, W3, b3, n_dev, n_max, fea_progress,      \
-                                                               view_progress, rgb, feat_out, st);                       \
+                                                               view_progress, rgb, feat_out, st, ahead);                \
     }
     if (split == 1 && !st) JT_LAUNCH_FWD(1, false, 2)
     else if (split == 1) JT_LAUNCH_FWD(1, true, 1)

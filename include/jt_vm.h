@@ -90,6 +90,23 @@ int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_facto
                      const float* samp, const int* slot, const int* n_dev, int n_max, const float* gin,
                      float* dsamp, int accumulate, cudaStream_t stream);
 
+/* Ray-walking form of the backward scatter used by the fused render op (vm_scatter.cu).
+ * Same factor-gradient semantics as jt_vm_gather_bwd, but (a) consecutive samples of a ray
+ * that fall into the same bilinear cell are merged in registers before one RED per corner
+ * (the marcher advances half a voxel per sample: tensorBase.py:483-484), and (b) instead of
+ * a per-sample dL/du it ACCUMULATES the pose-path gradients directly:
+ *   d_o[r] += sum_j dL/du_j * inv,   d_d[r] += sum_j dL/du_j * inv * t_j     (ray r = sidx/S)
+ * i.e. the autograd of rays_pts = o + d*t and normalize_coord (tensorBase.py:502-503,597).
+ * The element list must be ray-major (as jt_march_compact / jt_alpha_fwd produce it).
+ * d_o / d_d [N][3] must be initialised by the caller (zeros, or jt_ray_init for NDC rays). */
+int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,
+                       const float* samp, const int* slot, const int* sidx, const int* n_dev, int n_max,
+                       const float* gin, int n_samples, const float* h_inv, float* d_o, float* d_d,
+                       cudaStream_t stream);
+/* d_o = 0; d_d = dnorm_r / |d|^2 * d  (NDC rays: dists are scaled by |ray_dir|, batBase.py:63-65;
+ * dnorm holds dL/d|d| * |d| from jt_render_bwd) or 0 when dnorm is NULL. */
+int jt_ray_init(const float* rays_d, const float* dnorm, int n_rays, float* d_o, float* d_d, cudaStream_t stream);
+
 /* ---- K3: basis_mat + shading head (strict fp32 path) -------------------- */
 /* Y[m][0..N) = act(sum_k X[m][k] * W(n,k) + bias[n]) (* (mask[m][n] > 0)); W(n,k) =
  * W[n*ldw+k] (torch Linear weight) or W[k*ldw+n] if w_kn. act: 0 none, 1 relu,

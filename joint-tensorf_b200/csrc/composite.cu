@@ -262,6 +262,20 @@ __global__ void __launch_bounds__(256) ray_bwd_kernel(const int* __restrict__ of
     }
 }
 
+__global__ void ray_init_kernel(const float* __restrict__ rays_d, const float* __restrict__ dnorm, int n_rays,
+                                float* __restrict__ d_o, float* __restrict__ d_d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float k = 0.f, x = 0.f, y = 0.f, z = 0.f;
+    if (dnorm) {
+        x = rays_d[3 * r]; y = rays_d[3 * r + 1]; z = rays_d[3 * r + 2];
+        const float n2 = x * x + y * y + z * z;
+        k = n2 > 0.f ? dnorm[r] / n2 : 0.f;                        // dnorm holds dL/dnorm * norm
+    }
+    d_o[3 * r] = 0.f; d_o[3 * r + 1] = 0.f; d_o[3 * r + 2] = 0.f;
+    d_d[3 * r] = k * x; d_d[3 * r + 1] = k * y; d_d[3 * r + 2] = k * z;
+}
+
 static int ray_grid(int n_rays) {
     int want = (n_rays + 7) / 8;
     int cap = kNumSMs * 8;
@@ -324,5 +338,14 @@ extern "C" int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, con
     ray_bwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(ray_off, n_rays, reinterpret_cast<const float4*>(samp),
                                                          reinterpret_cast<const float4*>(dsamp), rays_d, dnorm,
                                                          h_inv[0], h_inv[1], h_inv[2], d_o, d_d);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_ray_init(const float* rays_d, const float* dnorm, int n_rays, float* d_o, float* d_d,
+                           cudaStream_t stream) {
+    JT_CHECK_ARG(rays_d && d_o && d_d);
+    if (n_rays <= 0) return JT_OK;
+    g_launches += 1;
+    ray_init_kernel<<<(n_rays + 255) / 256, 256, 0, stream>>>(rays_d, dnorm, n_rays, d_o, d_d);
     JT_RETURN_LAUNCH();
 }

@@ -100,4 +100,20 @@ __device__ __forceinline__ Tap make_tap(float g, int n) {
     return t;
 }
 
+// host: unpack the C-ABI factor description (include/jt_vm.h "Layouts")
+inline int fill_factors(Factors& F, const void* const* ptrs, const int* dims) {
+    int off = 0;
+    for (int i = 0; i < 3; ++i) {
+        F.plane[i] = static_cast<const float*>(ptrs[i]);
+        F.line[i] = static_cast<const float*>(ptrs[3 + i]);
+        F.H[i] = dims[i]; F.W[i] = dims[3 + i]; F.L[i] = dims[6 + i]; F.C[i] = dims[9 + i];
+        if (!F.plane[i] || !F.line[i]) return JT_ERR_ARG;
+        if (F.C[i] <= 0 || (F.C[i] & 3) || F.H[i] < 1 || F.W[i] < 1 || F.L[i] < 1) return JT_ERR_ARG;
+        F.off[i] = off;
+        off += F.C[i];
+    }
+    F.ctot = off;
+    return JT_OK;
+}
+
 }  // namespace jt

@@ -179,21 +179,6 @@ __global__ void __launch_bounds__(256) vm_bwd_kernel(Factors F, FactorGrads G, c
     }
 }
 
-static int fill_factors(Factors& F, const void* const* ptrs, const int* dims) {
-    int off = 0;
-    for (int i = 0; i < 3; ++i) {
-        F.plane[i] = static_cast<const float*>(ptrs[i]);
-        F.line[i] = static_cast<const float*>(ptrs[3 + i]);
-        F.H[i] = dims[i]; F.W[i] = dims[3 + i]; F.L[i] = dims[6 + i]; F.C[i] = dims[9 + i];
-        if (!F.plane[i] || !F.line[i]) return JT_ERR_ARG;
-        if (F.C[i] <= 0 || (F.C[i] & 3) || F.H[i] < 1 || F.W[i] < 1 || F.L[i] < 1) return JT_ERR_ARG;
-        F.off[i] = off;
-        off += F.C[i];
-    }
-    F.ctot = off;
-    return JT_OK;
-}
-
 static int grid_for(int n_hint) {
     long long want = ((long long)n_hint + 63) / 64;            // 64 samples per CTA pass
     long long cap = (long long)kNumSMs * 8;

@@ -159,6 +159,15 @@ def vm_gather_bwd(app, fs, gp, gl, samp, slot, n_dev, n_max, gin, dsamp, accumul
               "jt_vm_gather_bwd")
 
 
+def vm_scatter_rays(app, fs, gp, gl, samp, slot, sidx, n_dev, n_max, gin, n_samples, h_inv, d_o, d_d):
+    """Run-merged factor-gradient scatter + per-ray pose-path gradients (vm_scatter.cu)."""
+    gptrs = ptrs([g.data_ptr() for g in gp] + [g.data_ptr() for g in gl])
+    with TIMER.span("vm_app_bwd" if app else "vm_density_bwd"):
+        check(_lib.lib().jt_vm_scatter_rays(int(app), fs.ptrs, gptrs, fs.dims, _p(samp), _p(slot), _p(sidx),
+                                            _p(n_dev), int(n_max), _p(gin), int(n_samples), h_inv, _p(d_o), _p(d_d),
+                                            _stream()), "jt_vm_scatter_rays")
+
+
 # ------------------------------------------------------------------ K3
 def gemm_nt(x, ldx, w, ldw, w_kn, bias, y, ldy, mask, ldm, m_dev, m_max, n, k, act, name="gemm_nt",
             x_off=0, w_off=0, y_off=0, mask_off=0):

@@ -7,8 +7,8 @@ index):
   forward   jt_march_compact -> jt_vm_gather_fwd(density) -> jt_alpha_fwd
             -> jt_vm_gather_fwd(app) -> jt_gemm_nt(basis) -> shading head
             -> jt_composite_fwd
-  backward  jt_render_bwd -> jt_vm_gather_bwd(density) -> head backward
-            -> jt_vm_gather_bwd(app) -> jt_ray_bwd
+  backward  jt_render_bwd -> jt_ray_init -> jt_vm_scatter_rays(density) -> head backward
+            -> jt_vm_scatter_rays(app)      (pose-path gradients accumulate inside the scatters)
 
 Sample counts (V valid samples, A appearance samples) stay on the device; the
 kernels read them from `ray_off[N]` / `app_off[N]` and run persistent grids.
@@ -252,8 +252,12 @@ class VMRender(torch.autograd.Function):
             o += n
         gdp, gdl, gap, gal = views[0:3], views[3:6], views[6:9], views[9:12]
 
-        dsamp = torch.empty((cap, 4), device=dev)
-        ops.vm_gather_bwd(0, dfs, gdp, gdl, comp.samp, None, comp.count, cap, dsig, dsamp, 0)
+        d_o = torch.empty((N, 3), device=dev)
+        d_d = torch.empty((N, 3), device=dev)
+        with TIMER.span("ray_init"):
+            check(lib.jt_ray_init(_p(b["rays_d"]), _p(dnorm), N, _p(d_o), _p(d_d), _stream()), "jt_ray_init")
+        ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+                            cfg.h_inv, d_o, d_d)
 
         g_basis = torch.zeros_like(b["basis_w"])
         dcomps = torch.empty((cap, afs.ctot), device=dev)
@@ -269,13 +273,8 @@ class VMRender(torch.autograd.Function):
                         name="basis_bwd_w")
             ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
                         afs.ctot, F, 0, name="basis_bwd_x")
-        ops.vm_gather_bwd(1, afs, gap, gal, comp.samp, b["aidx"], b["a_count"], cap, dcomps, dsamp, 1)
-
-        d_o = torch.empty((N, 3), device=dev)
-        d_d = torch.empty((N, 3), device=dev)
-        with TIMER.span("ray_bwd"):
-            check(lib.jt_ray_bwd(_p(comp.ray_off), N, _p(comp.samp), _p(dsamp), _p(b["rays_d"]), _p(dnorm),
-                                 cfg.h_inv, _p(d_o), _p(d_d), _stream()), "jt_ray_bwd")
+        ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
+                            cfg.n_samples, cfg.h_inv, d_o, d_d)
 
         gdpn, gdln = FactorSet.grads_as_nchw(gdp, gdl)
         gapn, galn = FactorSet.grads_as_nchw(gap, gal)

@@ -19,6 +19,7 @@
 // are all the pose gradient needs) and flushed once per ray segment, so no per-sample
 // dL/du array is written and no separate ray_bwd pass is needed.
 #include <limits.h>
+#include <stdlib.h>
 #include "jt_common.cuh"
 #include "../../include/jt_vm.h"
 
@@ -60,119 +61,113 @@ struct ScatterArgs {
     int seg;                // samples per walker segment
 };
 
-// One walker = LW lanes = the LW channel quads of one plane (C = 4 LW). Work unit =
-// (segment of `seg` consecutive elements, plane i). Walkers are laid out over the CTA's
-// threads contiguously (they may straddle warps: no warp-level collectives are used).
-template <bool APP>
-__global__ void __launch_bounds__(256, 2) vm_scatter_walk_kernel(ScatterArgs A, int LW, int walkers_per_cta) {
+// One walker = LW lanes; lane `sub` owns the NQ channel quads sub, sub + LW, ... of a plane
+// (C = 4 LW NQ), i.e. per tap the walker's lanes read LW x 16 contiguous bytes NQ times.
+// Work unit = a segment of `seg` consecutive elements; the walker walks it once per plane
+// (plane index is a compile-time constant of walk_plane). Walkers are laid out over the
+// CTA's threads contiguously and use no warp-level collectives. The tap values are re-read
+// every step (L1 hits while the cell is unchanged: loads are ~5x cheaper per lane than
+// REDs); only the gradient accumulators live across steps.
+struct RaySums { float o[3], d[3]; };      // per axis: sum_j dL/du_j, sum_j dL/du_j * t_j (this lane's channels)
+
+template <bool APP, int NQ, int I>
+__device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
+                                           int& ray, int& ray_end, RaySums& rs) {
     const Factors& F = A.F;
-    const int n = A.n_dev ? *A.n_dev : A.n_fixed;
-    const int wl = threadIdx.x / LW;                     // walker within the CTA
-    const int q = (threadIdx.x - wl * LW) * 4;           // first channel of this lane's quad
-    if (wl >= walkers_per_cta) return;
-    const long long n_units = 3LL * ((n + A.seg - 1) / A.seg);
-    const long long stride = (long long)gridDim.x * walkers_per_cta;
-    for (long long unit = (long long)blockIdx.x * walkers_per_cta + wl; unit < n_units; unit += stride) {
-        const int i = (int)(unit % 3);
-        const int e0 = (int)(unit / 3) * A.seg;
-        const int e1 = min(e0 + A.seg, n);
-        const int W = F.W[i], H = F.H[i], L = F.L[i], C = F.C[i];
-        if (q >= C) continue;
-        const float* __restrict__ P = F.plane[i] + q;
-        const float* __restrict__ Ln = F.line[i] + q;
-        float* __restrict__ GP = A.G.plane[i] + q;
-        float* __restrict__ GL = A.G.line[i] + q;
-        const int ax = mat0(i), ay = mat1(i), al = vecm(i);
+    constexpr int ax = I == 2 ? 1 : 0, ay = I == 0 ? 1 : 2, al = 2 - I;      // matMode / vecMode (tensorBase.py:405-406)
+    const int W = F.W[I], H = F.H[I], L = F.L[I], C = F.C[I];
+    if (q >= C) return;
+    const float* __restrict__ P = F.plane[I] + q;
+    const float* __restrict__ Ln = F.line[I] + q;
+    float* __restrict__ GP = A.G.plane[I] + q;
+    float* __restrict__ GL = A.G.line[I] + q;
+    const float* __restrict__ gbase = APP ? A.gin + F.off[I] + q : A.gin;
+    const float sclx = 0.5f * (float)(W - 1), scly = 0.5f * (float)(H - 1), scll = 0.5f * (float)(L - 1);
 
-        // current plane cell / line cell state
-        int cx = INT_MIN, cy = INT_MIN, cl = INT_MIN;
-        unsigned o00 = 0, o10 = 0, o01 = 0, o11 = 0, ol0 = 0, ol1 = 0;   // element offsets (< 2^31, checked on the host)
-        float mx0 = 0.f, mx1 = 0.f, my0 = 0.f, my1 = 0.f, ml0 = 0.f, ml1 = 0.f;     // in-range masks
-        float4 a = f4z(), b = f4z(), c = f4z(), d = f4z(), la = f4z(), lb = f4z();
-        float4 g00 = f4z(), g10 = f4z(), g01 = f4z(), g11 = f4z(), gl0 = f4z(), gl1 = f4z();
-        // per-ray coordinate-gradient sums
-        int ray = -1;
-        int ray_end = -1;
-        float so = 0.f, sdx = 0.f;   // axis ax:  sum du, sum du*t
-        float sp = 0.f, sdy = 0.f;   // axis ay
-        float sq = 0.f, sdl = 0.f;   // axis al
+    // accumulated cell: indices and clamped element offsets
+    int cx = INT_MIN, cy = INT_MIN, cl = INT_MIN;
+    unsigned s00 = 0, s10 = 0, s01 = 0, s11 = 0, sl0 = 0, sl1 = 0;
+    float4 g00[NQ], g10[NQ], g01[NQ], g11[NQ], gl0[NQ], gl1[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) { g00[k] = g10[k] = g01[k] = g11[k] = gl0[k] = gl1[k] = f4z(); }
 
-        auto flush_plane = [&]() {
-            if (mx0 * my0 != 0.f && f4_any(g00)) red_add_v4(GP + o00, g00);
-            if (mx1 * my0 != 0.f && f4_any(g10)) red_add_v4(GP + o10, g10);
-            if (mx0 * my1 != 0.f && f4_any(g01)) red_add_v4(GP + o01, g01);
-            if (mx1 * my1 != 0.f && f4_any(g11)) red_add_v4(GP + o11, g11);
-            g00 = f4z(); g10 = f4z(); g01 = f4z(); g11 = f4z();
-        };
-        auto flush_line = [&]() {
-            if (ml0 != 0.f && f4_any(gl0)) red_add_v4(GL + ol0, gl0);
-            if (ml1 != 0.f && f4_any(gl1)) red_add_v4(GL + ol1, gl1);
-            gl0 = f4z(); gl1 = f4z();
-        };
-        auto flush_ray = [&]() {
-            if (ray >= 0) {
-                const float ix = A.inv[ax], iy = A.inv[ay], il = A.inv[al];
-                if (so != 0.f) atomicAdd(A.d_o + 3 * ray + ax, so * ix);
-                if (sp != 0.f) atomicAdd(A.d_o + 3 * ray + ay, sp * iy);
-                if (sq != 0.f) atomicAdd(A.d_o + 3 * ray + al, sq * il);
-                if (sdx != 0.f) atomicAdd(A.d_d + 3 * ray + ax, sdx * ix);
-                if (sdy != 0.f) atomicAdd(A.d_d + 3 * ray + ay, sdy * iy);
-                if (sdl != 0.f) atomicAdd(A.d_d + 3 * ray + al, sdl * il);
+    auto flush_ray = [&]() {
+        if (ray >= 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (rs.o[a] != 0.f) atomicAdd(A.d_o + 3 * ray + a, rs.o[a] * A.inv[a]);
+                if (rs.d[a] != 0.f) atomicAdd(A.d_d + 3 * ray + a, rs.d[a] * A.inv[a]);
             }
-            so = sdx = sp = sdy = sq = sdl = 0.f;
-        };
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
+    };
 
-        // software pipeline: the sample record of element e+1 is fetched while e is processed
-        int jn = 0, sn = 0;
-        float4 un = f4z();
-        if (e0 < e1) {
-            jn = A.slot ? A.slot[e0] : e0;
+    // software pipeline: the sample record of element e+1 is fetched while e is processed
+    int jn = A.slot ? A.slot[e0] : e0;
+    float4 un = A.samp[jn];
+    int sn = A.sidx[jn];
+    for (int e = e0; e < e1; ++e) {
+        const float4 u4 = un;
+        const int sid = sn;
+        if (e + 1 < e1) {
+            jn = A.slot ? A.slot[e + 1] : e + 1;
             un = A.samp[jn];
             sn = A.sidx[jn];
         }
-        for (int e = e0; e < e1; ++e) {
-            const float4 u4 = un;
-            const int sid = sn;
-            if (e + 1 < e1) {
-                jn = A.slot ? A.slot[e + 1] : e + 1;
-                un = A.samp[jn];
-                sn = A.sidx[jn];
+        const float u[3] = {u4.x, u4.y, u4.z};
+        if (sid >= ray_end || sid < ray_end - A.S) {          // another ray (lists are ray-major)
+            flush_ray();
+            ray = sid / A.S;
+            ray_end = (ray + 1) * A.S;
+        }
+        // tap positions (ATen grid_sampler, align_corners=True, zeros padding)
+        const float fxp = (u[ax] + 1.0f) * sclx, fyp = (u[ay] + 1.0f) * scly, flp = (u[al] + 1.0f) * scll;
+        const float xf = floorf(fxp), yf = floorf(fyp), lf = floorf(flp);
+        const int x0 = (int)fminf(fmaxf(xf, -2.0f), (float)W), y0 = (int)fminf(fmaxf(yf, -2.0f), (float)H),
+                  l0 = (int)fminf(fmaxf(lf, -2.0f), (float)L);        // NaN -> -2: both taps out of range
+        const float mx0 = (x0 >= 0 && x0 < W) ? 1.f : 0.f, mx1 = (x0 + 1 >= 0 && x0 + 1 < W) ? 1.f : 0.f;
+        const float my0 = (y0 >= 0 && y0 < H) ? 1.f : 0.f, my1 = (y0 + 1 >= 0 && y0 + 1 < H) ? 1.f : 0.f;
+        const float ml0 = (l0 >= 0 && l0 < L) ? 1.f : 0.f, ml1 = (l0 + 1 >= 0 && l0 + 1 < L) ? 1.f : 0.f;
+        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+        const unsigned o00 = (unsigned)((yc0 * W + xc0) * C), o10 = (unsigned)((yc0 * W + xc1) * C);
+        const unsigned o01 = (unsigned)((yc1 * W + xc0) * C), o11 = (unsigned)((yc1 * W + xc1) * C);
+        const unsigned ol0 = (unsigned)(min(max(l0, 0), L - 1) * C), ol1 = (unsigned)(min(max(l0 + 1, 0), L - 1) * C);
+        if (x0 != cx || y0 != cy) {                          // plane cell changed: flush the 4 corners
+            if (cx != INT_MIN) {
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) {
+                    red_add_v4(GP + s00 + k * qs, g00[k]); red_add_v4(GP + s10 + k * qs, g10[k]);
+                    red_add_v4(GP + s01 + k * qs, g01[k]); red_add_v4(GP + s11 + k * qs, g11[k]);
+                }
             }
-            const float u[3] = {u4.x, u4.y, u4.z};
-            if (sid >= ray_end || ray < 0) {          // new ray (lists are ray-major)
-                flush_ray();
-                ray = sid / A.S;
-                ray_end = (ray + 1) * A.S;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) { g00[k] = f4z(); g10[k] = f4z(); g01[k] = f4z(); g11[k] = f4z(); }
+            cx = x0; cy = y0; s00 = o00; s10 = o10; s01 = o01; s11 = o11;
+        }
+        if (l0 != cl) {                                      // line cell changed
+            if (cl != INT_MIN) {
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) { red_add_v4(GL + sl0 + k * qs, gl0[k]); red_add_v4(GL + sl1 + k * qs, gl1[k]); }
             }
-            const Pos px = axis_pos(u[ax], W), py = axis_pos(u[ay], H), pl = axis_pos(u[al], L);
-            if (px.i0 != cx || py.i0 != cy) {
-                flush_plane();
-                cx = px.i0; cy = py.i0;
-                const int x0 = cx, x1 = cx + 1, y0 = cy, y1 = cy + 1;
-                mx0 = (x0 >= 0 && x0 < W) ? 1.f : 0.f; mx1 = (x1 >= 0 && x1 < W) ? 1.f : 0.f;
-                my0 = (y0 >= 0 && y0 < H) ? 1.f : 0.f; my1 = (y1 >= 0 && y1 < H) ? 1.f : 0.f;
-                const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x1, 0), W - 1);
-                const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y1, 0), H - 1);
-                o00 = (unsigned)((yc0 * W + xc0) * C); o10 = (unsigned)((yc0 * W + xc1) * C);
-                o01 = (unsigned)((yc1 * W + xc0) * C); o11 = (unsigned)((yc1 * W + xc1) * C);
-                a = ldg4(P + o00); b = ldg4(P + o10); c = ldg4(P + o01); d = ldg4(P + o11);
-            }
-            if (pl.i0 != cl) {
-                flush_line();
-                cl = pl.i0;
-                const int l0 = cl, l1 = cl + 1;
-                ml0 = (l0 >= 0 && l0 < L) ? 1.f : 0.f; ml1 = (l1 >= 0 && l1 < L) ? 1.f : 0.f;
-                ol0 = (unsigned)(min(max(l0, 0), L - 1) * C); ol1 = (unsigned)(min(max(l1, 0), L - 1) * C);
-                la = ldg4(Ln + ol0); lb = ldg4(Ln + ol1);
-            }
-            float4 g4;
-            if (APP) g4 = __ldcs(reinterpret_cast<const float4*>(A.gin + (size_t)e * F.ctot + F.off[i] + q));
-            else { const float gs = A.gin[e]; g4 = make_float4(gs, gs, gs, gs); }
-
-            const float wx0 = (1.f - px.f) * mx0, wx1 = px.f * mx1;
-            const float wy0 = (1.f - py.f) * my0, wy1 = py.f * my1;
-            const float wl0 = (1.f - pl.f) * ml0, wl1 = pl.f * ml1;
-            const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) { gl0[k] = f4z(); gl1[k] = f4z(); }
+            cl = l0; sl0 = ol0; sl1 = ol1;
+        }
+        const float fx = fxp - xf, fy = fyp - yf, fl = flp - lf;
+        const float wx0 = (1.f - fx) * mx0, wx1 = fx * mx1, wy0 = (1.f - fy) * my0, wy1 = fy * my1;
+        const float wl0 = (1.f - fl) * ml0, wl1 = fl * ml1;
+        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+        float dA = 0.f, dB = 0.f, dC = 0.f, dD = 0.f, dLa = 0.f, dLb = 0.f;      // sum_c gl*tap / gp*tap
+        const float gs = APP ? 0.f : gbase[e];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const float4 a = ldg4(P + o00 + k * qs), b = ldg4(P + o10 + k * qs);
+            const float4 c = ldg4(P + o01 + k * qs), d = ldg4(P + o11 + k * qs);
+            const float4 la = ldg4(Ln + ol0 + k * qs), lb = ldg4(Ln + ol1 + k * qs);
+            const float4 g4 = APP ? __ldcs(reinterpret_cast<const float4*>(gbase + (size_t)e * F.ctot + k * qs))
+                                  : make_float4(gs, gs, gs, gs);
             float4 pv, lv;
             pv.x = a.x * w00 + b.x * w10 + c.x * w01 + d.x * w11; pv.y = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
             pv.z = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11; pv.w = a.w * w00 + b.w * w10 + c.w * w01 + d.w * w11;
@@ -180,26 +175,54 @@ __global__ void __launch_bounds__(256, 2) vm_scatter_walk_kernel(ScatterArgs A, 
             lv.z = la.z * wl0 + lb.z * wl1; lv.w = la.w * wl0 + lb.w * wl1;
             const float4 gl = f4_mul2(g4, lv);       // dL/dP (interpolated plane value)
             const float4 gp = f4_mul2(g4, pv);       // dL/dL (interpolated line value)
-            f4_fma(g00, gl, w00); f4_fma(g10, gl, w10); f4_fma(g01, gl, w01); f4_fma(g11, gl, w11);
-            f4_fma(gl0, gp, wl0); f4_fma(gl1, gp, wl1);
-            // d/d index (ATen grid_sampler_2d_backward: out-of-range taps read as 0)
-            float4 dpx, dpy, dl;
-#define JT_DP(k)                                                                                         \
-            dpx.k = (b.k * mx1 - a.k * mx0) * wy0 + (d.k * mx1 - c.k * mx0) * wy1;                       \
-            dpy.k = (c.k * my1 - a.k * my0) * wx0 + (d.k * my1 - b.k * my0) * wx1;                       \
-            dl.k = lb.k * ml1 - la.k * ml0;
-            JT_DP(x) JT_DP(y) JT_DP(z) JT_DP(w)
-#undef JT_DP
-            const float t = u4.w;
-            const float dux = f4_dot2(gl, dpx) * px.scale, duy = f4_dot2(gl, dpy) * py.scale,
-                        dul = f4_dot2(gp, dl) * pl.scale;
-            so += dux; sdx = fmaf(dux, t, sdx);
-            sp += duy; sdy = fmaf(duy, t, sdy);
-            sq += dul; sdl = fmaf(dul, t, sdl);
+            f4_fma(g00[k], gl, w00); f4_fma(g10[k], gl, w10); f4_fma(g01[k], gl, w01); f4_fma(g11[k], gl, w11);
+            f4_fma(gl0[k], gp, wl0); f4_fma(gl1[k], gp, wl1);
+            dA += f4_dot2(gl, a); dB += f4_dot2(gl, b); dC += f4_dot2(gl, c); dD += f4_dot2(gl, d);
+            dLa += f4_dot2(gp, la); dLb += f4_dot2(gp, lb);
         }
-        flush_plane();
-        flush_line();
-        flush_ray();
+        // d/d index (ATen grid_sampler_2d_backward: out-of-range taps read as 0)
+        const float dux = ((dB * mx1 - dA * mx0) * wy0 + (dD * mx1 - dC * mx0) * wy1) * sclx;
+        const float duy = ((dC * my1 - dA * my0) * wx0 + (dD * my1 - dB * my0) * wx1) * scly;
+        const float dul = (dLb * ml1 - dLa * ml0) * scll;
+        const float t = u4.w;
+        rs.o[ax] += dux; rs.d[ax] = fmaf(dux, t, rs.d[ax]);
+        rs.o[ay] += duy; rs.d[ay] = fmaf(duy, t, rs.d[ay]);
+        rs.o[al] += dul; rs.d[al] = fmaf(dul, t, rs.d[al]);
+    }
+    if (cx != INT_MIN) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            red_add_v4(GP + s00 + k * qs, g00[k]); red_add_v4(GP + s10 + k * qs, g10[k]);
+            red_add_v4(GP + s01 + k * qs, g01[k]); red_add_v4(GP + s11 + k * qs, g11[k]);
+        }
+    }
+    if (cl != INT_MIN) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) { red_add_v4(GL + sl0 + k * qs, gl0[k]); red_add_v4(GL + sl1 + k * qs, gl1[k]); }
+    }
+    flush_ray();
+}
+
+template <bool APP, int NQ, int MINB>
+__global__ void __launch_bounds__(128, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
+    const int LW = NQ > 1 ? 4 : LW_rt;                   // multi-quad lanes: 4 lanes per walker, compile-time strides
+    const int n = A.n_dev ? *A.n_dev : A.n_fixed;
+    const int wl = threadIdx.x / LW;                     // walker within the CTA
+    const int q = (threadIdx.x - wl * LW) * 4;           // first channel of this lane's first quad
+    const int qs = LW * 4;                               // channel stride between this lane's quads
+    if (wl >= walkers_per_cta) return;
+    const int n_units = (n + A.seg - 1) / A.seg;
+    const int stride = gridDim.x * walkers_per_cta;
+    for (int unit = blockIdx.x * walkers_per_cta + wl; unit < n_units; unit += stride) {
+        const int e0 = unit * A.seg;
+        const int e1 = min(e0 + A.seg, n);
+        int ray = -1, ray_end = INT_MIN;
+        RaySums rs;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
+        walk_plane<APP, NQ, 0>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 1>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 2>(A, e0, e1, q, qs, ray, ray_end, rs);
     }
 }
 
@@ -230,16 +253,25 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     for (int a = 0; a < 3; ++a) A.inv[a] = h_inv[a];
     A.S = n_samples;
     A.seg = 32;
-    const int LW = cmax / 4;                                  // lanes per walker
-    JT_CHECK_ARG(LW >= 1 && LW <= 256);
-    int wpc = 256 / LW;                                       // walkers per CTA (<= 256 threads, 2 CTAs per SM)
-    int threads = ((wpc * LW + 31) / 32) * 32;
-    long long units = 3LL * (((long long)n_max + A.seg - 1) / A.seg);
+    // lanes per walker / quads per lane: uniform C in {16, 32, 48} -> 4 lanes x C/16 quads, else one quad per lane
+    int nq = 1, LW = cmax / 4;
+    if (A.F.C[0] == A.F.C[1] && A.F.C[1] == A.F.C[2] && cmax % 16 == 0 && cmax <= 48) { nq = cmax / 16; LW = 4; }
+    static const char* env_mode0 = getenv("JT_SC_MODE");
+    if (env_mode0 && atoi(env_mode0) == 1 && nq > 1) { nq = 1; LW = cmax / 4; }
+    JT_CHECK_ARG(LW >= 1 && LW <= 128);
+    const int wpc = 128 / LW;                                 // walkers per CTA
+    const int threads = ((wpc * LW + 31) / 32) * 32;
+    long long units = ((long long)n_max + A.seg - 1) / A.seg;
     long long want = (units + wpc - 1) / wpc;
-    long long cap = (long long)kNumSMs * 16;
+    long long cap = (long long)kNumSMs * 32;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
-    if (app) vm_scatter_walk_kernel<true><<<grid, threads, 0, stream>>>(A, LW, wpc);
-    else vm_scatter_walk_kernel<false><<<grid, threads, 0, stream>>>(A, LW, wpc);
+    static const char* env_mode = getenv("JT_SC_MODE");       // tuning: 1 = one quad per lane, 2 = 3 quads at 168 regs
+    const int mode = env_mode ? atoi(env_mode) : 0;
+    if (mode == 1 && nq > 1) { nq = 1; LW = cmax / 4; }
+#define JT_SC(APPV, NQV, MB) vm_scatter_walk_kernel<APPV, NQV, MB><<<grid, threads, 0, stream>>>(A, LW, wpc)
+    if (app) { if (nq == 3 && mode == 2) JT_SC(true, 3, 3); else if (nq == 3) JT_SC(true, 3, 2); else if (nq == 2) JT_SC(true, 2, 3); else JT_SC(true, 1, 3); }
+    else { if (nq == 3 && mode == 2) JT_SC(false, 3, 3); else if (nq == 3) JT_SC(false, 3, 2); else if (nq == 2) JT_SC(false, 2, 3); else JT_SC(false, 1, 3); }
+#undef JT_SC
     JT_RETURN_LAUNCH();
 }

@@ -151,12 +151,27 @@ int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* si
                    const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
                    float fea_progress, float view_progress, float* rgb, float* feat_out, void* stage,
                    cudaStream_t stream);
-/* Backward of jt_head_fwd_tc (bf16 tensor-core GEMMs, fp32 accumulation in TMEM): from dout
- * [A][4] (gradient at the head's pre-activation, from jt_render_bwd), feat [A][28] and the
+/* The same head as two kernels, the form the fused render op uses:
+ * jt_app_basis_fwd_tc = appearance gather (bateRF.py:97-128) + basis_mat (tensoRF.py:270) per tile
+ * of 128 samples: the plane x line products go straight into the bf16 shared-memory operand tile
+ * (never to HBM in fp32), one tcgen05 GEMM projects them; out featdir [A][32] = feat 0..26 | 0 |
+ * view dir 28..30 | 0. Needs 3 x 48 appearance components and app_dim 27. `stage` (training)
+ * receives the bf16 component tile for the basis_mat weight gradient.
+ * jt_head_mlp_fwd_tc = positional_encoding + MLPRender_Fea (tensorBase.py:43-55,116-126) on those
+ * rows -> rgb [A][4]; `stage` receives the encoded-input / relu(h1) / relu(h2) tiles. */
+int jt_app_basis_fwd_tc(int split, const void* const* h_factors, const int* h_dims, const float* samp,
+                        const int* aidx, const int* sidx, const float* rays_d, int n_samples, int normalize_dir,
+                        const float* Wb, const int* n_dev, int n_max, float* featdir, void* stage,
+                        cudaStream_t stream);
+int jt_head_mlp_fwd_tc(int split, const float* featdir, const float* W1, const float* b1, const float* W2,
+                       const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
+                       float fea_progress, float view_progress, float* rgb, void* stage, cudaStream_t stream);
+/* Backward of the tensor-core head (bf16 tensor-core GEMMs, fp32 accumulation in TMEM): from dout
+ * [A][4] (gradient at the head's pre-activation, from jt_render_bwd), feat [A][ldf] and the
  * tiles the forward left in `stage`, computes dcomps [A][144] (for jt_vm_gather_bwd) and ADDS
  * the weight gradients into gWb [27][144], gW1 [64][150], gb1, gW2 [64][64], gb2, gW3 [3][64],
  * gb3. relu masks are the forward's own; nothing is recomputed. */
-int jt_head_bwd_tc(const float* dout, const float* feat, const float* Wb, const float* W1, const float* W2,
+int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, const float* Wb, const float* W1, const float* W2,
                    const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps, void* stage,
                    float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                    cudaStream_t stream);

@@ -92,6 +92,17 @@ __device__ __forceinline__ void stage_tile(unsigned char* hi, unsigned char* lo,
 // clamp(progress*2 - l, 0, 1).
 struct PEMask { float f0, f1, v0, v1; };
 
+// sin/cos with a two-constant Cody-Waite reduction to [-pi, pi] and the SFU approximations
+// (abs error ~2^-21 there): well below the 2^-17 relative precision of the hi+lo bf16 operands.
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);
+    r = fmaf(k, 1.7484556000744883e-7f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
+template <bool FAST = false>
 __device__ __forceinline__ void encode_chunk(int chunk, const float feat[32], const float dir[3], const PEMask& pm,
                                              float v[8]) {
     if (chunk < 4) {
@@ -107,7 +118,7 @@ __device__ __forceinline__ void encode_chunk(int chunk, const float feat[32], co
             const bool is_view = e >= F_;
             const float src = is_view ? dir[e - F_] : feat[e];
             float s, co;
-            sincosf(src, &s, &co);
+            if (FAST) fast_sincos(src, &s, &co); else sincosf(src, &s, &co);
             const float m0 = is_view ? pm.v0 : pm.f0, m1 = is_view ? pm.v1 : pm.f1;
             v[4 * h + 0] = s * m0;
             v[4 * h + 1] = (2.f * s * co) * m1;
@@ -129,6 +140,8 @@ constexpr int OFF_D2 = OFF_A3 + SZ_A3, OFF_D1 = OFF_D2 + SZ_D2, OFF_DF = OFF_D1 
 constexpr int STAGE_TILE_BYTES = OFF_DO + SZ_DO;        // 161792
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+constexpr int FD = 32;    // floats per feat/dir row written by app_basis_fwd_kernel: feat 0..26 | 27 pad | dir 28..30 | 31 pad
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {

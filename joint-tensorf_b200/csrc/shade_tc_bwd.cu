@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint4 q) {
 constexpr int NTB = 2 * TM;     // two threads per sample row (column halves), as in the forward kernel
 
 __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
-    const float* __restrict__ dout, const float* __restrict__ feat_in, const float* __restrict__ Wb,
+    const float* __restrict__ dout, const float* __restrict__ feat_in, int ldf, const float* __restrict__ Wb,
     const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
     const int* __restrict__ n_dev, int n_fixed, float fprog, float* __restrict__ dcomps,
     unsigned char* __restrict__ stage) {
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
                 q3[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + o));
                 q2[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + o));
             }
-            const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * 28) + 4 * hh;
+            const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * ldf) + 4 * hh;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -358,11 +358,11 @@ extern "C" long long jt_head_tc_stage_bytes(int n_max) {
     return (((long long)n_max + TM - 1) / TM) * STAGE_TILE_BYTES;
 }
 
-extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, const float* Wb, const float* W1, const float* W2,
+extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, const float* Wb, const float* W1, const float* W2,
                               const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps,
                               void* stage, float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
                               float* gb3, cudaStream_t stream) {
-    JT_CHECK_ARG(dout && feat && Wb && W1 && W2 && W3 && dcomps && stage);
+    JT_CHECK_ARG(dout && feat && Wb && W1 && W2 && W3 && dcomps && stage && ldf >= 28 && ldf % 4 == 0);
     JT_CHECK_ARG(gWb && gW1 && gb1 && gW2 && gb2 && gW3 && gb3);
     JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
     if (n_max <= 0) return JT_OK;
@@ -372,7 +372,7 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, const float*
     if (int rc = set_smem(head_bwd_data_kernel, BwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_wgrad_kernel, WG_STAGES * WG_STAGE_BYTES)) return rc;
     g_launches += 2;
-    head_bwd_data_kernel<<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, Wb, W1, W2, W3, n_dev, n_max, fea_progress,
+    head_bwd_data_kernel<<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max, fea_progress,
                                                                  dcomps, static_cast<unsigned char*>(stage));
     head_bwd_wgrad_kernel<<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(static_cast<const unsigned char*>(stage),
                                                                               n_dev, n_max, gWb, gW1, gb1, gW2, gb2,

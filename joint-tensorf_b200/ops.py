@@ -223,10 +223,27 @@ def head_fwd_tc(split, comps, aidx, sidx, rays_d, n_samples, normalize_dir, wb, 
                                         _p(stage), _stream()), "jt_head_fwd_tc")
 
 
+def app_basis_fwd_tc(split, fs, samp, aidx, sidx, rays_d, n_samples, normalize_dir, wb, n_dev, n_max, featdir,
+                     stage=None):
+    """appearance gather + basis_mat on tensor cores -> featdir [A][32] (feat | dir)."""
+    with TIMER.span("app_basis_fwd_tc"):
+        check(_lib.lib().jt_app_basis_fwd_tc(split, fs.ptrs, fs.dims, _p(samp), _p(aidx), _p(sidx), _p(rays_d),
+                                             int(n_samples), int(normalize_dir), _p(wb), _p(n_dev), int(n_max),
+                                             _p(featdir), _p(stage), _stream()), "jt_app_basis_fwd_tc")
+
+
+def head_mlp_fwd_tc(split, featdir, w1, b1, w2, b2, w3, b3, n_dev, n_max, fprog, vprog, rgb, stage=None):
+    with TIMER.span("head_mlp_fwd_tc"):
+        check(_lib.lib().jt_head_mlp_fwd_tc(split, _p(featdir), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
+                                            _p(n_dev), int(n_max), float(fprog), float(vprog), _p(rgb), _p(stage),
+                                            _stream()), "jt_head_mlp_fwd_tc")
+
+
 def head_bwd_tc(dout, feat, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, grads):
-    """grads = (gWb, gW1, gb1, gW2, gb2, gW3, gb3), zero-initialised by the caller."""
+    """grads = (gWb, gW1, gb1, gW2, gb2, gW3, gb3), zero-initialised by the caller.
+    feat: [A][ldf] rows whose first 27 floats are the basis projection (ldf = 28 or 32)."""
     with TIMER.span("head_bwd_tc"):
-        check(_lib.lib().jt_head_bwd_tc(_p(dout), _p(feat), _p(wb), _p(w1), _p(w2), _p(w3), _p(n_dev), int(n_max),
+        check(_lib.lib().jt_head_bwd_tc(_p(dout), _p(feat), int(feat.shape[1]), _p(wb), _p(w1), _p(w2), _p(w3), _p(n_dev), int(n_max),
                                         float(fprog), _p(dcomps), _p(stage), *[_p(g) for g in grads], _stream()),
               "jt_head_bwd_tc")
 

@@ -183,18 +183,21 @@ class VMRender(torch.autograd.Function):
                                    _p(app_of), _stream()), "jt_alpha_fwd")
         a_count = app_off[N:N + 1]
 
-        comps = torch.empty((cap, afs.ctot), device=dev)
-        ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
         ws = {}
+        comps = None
         if cfg.head == "tc":
             tc_supported(cfg, afs, raise_if_not=True)
             rgb = torch.empty((cap, 4), device=dev)
             train = any(ctx.needs_input_grad)
-            feat = torch.empty((cap, 28), device=dev) if train else None
+            feat = torch.empty((cap, 32), device=dev)             # feat 0..26 | 0 | view dir 28..30 | 0
             ws["stage"] = ops.head_tc_stage(cap, dev) if train else None
-            ops.head_fwd_tc(cfg.tc_fwd_split, comps, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w, *head, a_count, cap,
-                            cfg.fea_prog, cfg.view_prog, rgb, feat, ws["stage"])
+            ops.app_basis_fwd_tc(cfg.tc_fwd_split, afs, comp.samp, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w,
+                                 a_count, cap, feat, ws["stage"])
+            ops.head_mlp_fwd_tc(cfg.tc_fwd_split, feat, *head, a_count, cap, cfg.fea_prog, cfg.view_prog, rgb,
+                                ws["stage"])
         else:
+            comps = torch.empty((cap, afs.ctot), device=dev)
+            ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
             feat = torch.empty((cap, ldf), device=dev)
             ops.gemm_nt(comps, afs.ctot, basis_w, afs.ctot, 0, None, feat, ldf, None, 0, a_count, cap, F, afs.ctot, 0,
                         name="basis_fwd")

@@ -32,9 +32,6 @@ struct GSmem {
 };
 
 __device__ __forceinline__ uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
-__device__ __forceinline__ float4 resid4(float4 v) {
-    return make_float4(bf16_resid(v.x), bf16_resid(v.y), bf16_resid(v.z), bf16_resid(v.w));
-}
 
 template <int SPLIT, bool SAVE>
 __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const float4* __restrict__ samp,
@@ -101,8 +98,14 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
                 v.w = (a.w * w00 + b.w * w10 + c.w * w01 + d.w * w11) * (la.w * tl.w0 + lb.w * tl.w1);
                 const int c0 = i * (CT / 3) + 16 * k + 4 * sub;                 // first channel of this quad
                 const int off = (c0 >> 3) * (TM * 16) + r * 16 + ((c0 >> 2) & 1) * 8;
-                *reinterpret_cast<uint2*>(a_hi + off) = pack4_bf16(v);
-                if (SPLIT == 2) *reinterpret_cast<uint2*>(a_lo + off) = pack4_bf16(resid4(v));
+                if (SPLIT == 2) {
+                    uint2 h, l;
+                    split_pair(v.x, v.y, h.x, l.x); split_pair(v.z, v.w, h.y, l.y);
+                    *reinterpret_cast<uint2*>(a_hi + off) = h;
+                    *reinterpret_cast<uint2*>(a_lo + off) = l;
+                } else {
+                    *reinterpret_cast<uint2*>(a_hi + off) = pack4_bf16(v);
+                }
             }
         }
         // view direction of the sample (viewdirs = ray_dir, normalised for NDC rays: batBase.py:63-66)

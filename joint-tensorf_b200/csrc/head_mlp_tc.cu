@@ -4,8 +4,8 @@
 // Replaces reference positional_encoding (tensorBase.py:43-55) and MLPRender_Fea.forward
 // (tensorBase.py:116-126) for app_dim 27 / hidden 64 / pe 2 (the Blender configs).
 //
-// Per tile (two threads per sample row, each owning half of the columns):
-//   feat/dir row (128 B, prefetched one tile ahead) -> PE -> bf16 tile A1 [128x160]
+// Per tile (four threads per sample row, each owning a quarter of the columns):
+//   feat/dir row (prefetched one tile ahead)        -> PE -> bf16 tile A1 [128x160]
 //                                                    MMA: h1 = A1 * W1^T   [128x64] (TMEM)
 //   relu(h1) -> bf16 tile A2 [128x80]                MMA: h2 = A2 * W2^T   [128x64] (TMEM)
 //   relu(h2) -> layer 3 (3x64 dot products in registers) -> sigmoid -> rgb
@@ -33,7 +33,16 @@ struct HSmem {
     static constexpr int total = off_w3 + (3 * H_ + 4) * 4;
 };
 
-constexpr int HT = 2 * TM;      // thread (r, hh): r = tid & 127 = tile row = TMEM lane, hh = tid >> 7 = column half
+constexpr int HQ = 4;           // threads per sample row (column quarters): 16 warps keep the SIMT phases latency-tolerant
+constexpr int HT = HQ * TM;     // thread (r, hq): r = tid & 127 = tile row = TMEM lane, hq = tid >> 7
+
+// chunks of the encoded input owned by column-quarter hq: the 15 PE chunks (two sin/cos
+// elements each) are spread 3/4/4/4, the 4 raw chunks go with the short PE share, the
+// zero chunk 19 with the last
+__device__ __forceinline__ void chunk_range(int hq, int& c0, int& c1) {
+    c0 = hq == 0 ? 0 : 3 + 4 * hq;
+    c1 = hq == 3 ? 20 : 7 + 4 * hq;
+}
 
 template <int SPLIT, bool SAVE>
 __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restrict__ featdir, const float* __restrict__ W1,
@@ -46,9 +55,9 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
-    __shared__ float part[TM][3];                 // layer-3 partial sums of the hh = 1 half
+    __shared__ float part[2][HQ - 1][TM][3];      // layer-3 partial sums of column quarters 1..3, double-buffered
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & (TM - 1), hh = tid >> 7;
+    const int r = tid & (TM - 1), hq = tid >> 7;
     const int n = n_dev ? *n_dev : n_fixed;
 
     unsigned char* w1_hi = smem + L::off_w1;  unsigned char* w1_lo = SPLIT == 2 ? w1_hi + L::W1 : nullptr;
@@ -74,15 +83,25 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
     PEMask pm;
     pm.f0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f); pm.f1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
     pm.v0 = fminf(fmaxf(vprog * 2.f - 0.f, 0.f), 1.f); pm.v1 = fminf(fmaxf(vprog * 2.f - 1.f, 0.f), 1.f);
+    int ec0, ec1, pb = 0;
+    chunk_range(hq, ec0, ec1);
 
-    // the 128-byte feat/dir row of the NEXT tile is fetched while the current tile computes
-    float4 nx[8];
+    // the feat/dir row of the NEXT tile is fetched while the current tile computes. Only the 30
+    // floats that are used are loaded: a dead destination register would be recycled by the
+    // compiler while its load is still in flight and stall the consumer (seen in ncu).
+    float4 nx[6];
+    float2 nf2, nd2;
+    float nf1, nd1;
     auto prefetch = [&](long long t) {
         const long long rw = t * TM + r;
         const bool lv = rw < n;
-        const float4* src = reinterpret_cast<const float4*>(featdir + (size_t)(lv ? rw : 0) * FD);
+        const float* src = featdir + (size_t)(lv ? rw : 0) * FD;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) nx[c] = lv ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 6; ++c) nx[c] = lv ? __ldcs(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nf2 = lv ? __ldcs(reinterpret_cast<const float2*>(src + 24)) : make_float2(0.f, 0.f);
+        nf1 = lv ? __ldcs(src + 26) : 0.f;
+        nd2 = lv ? __ldcs(reinterpret_cast<const float2*>(src + 28)) : make_float2(0.f, 0.f);
+        nd1 = lv ? __ldcs(src + 30) : 0.f;
     };
     prefetch(blockIdx.x);
 
@@ -92,21 +111,15 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
         unsigned char* st = SAVE ? stage + (size_t)tile * STAGE_TILE_BYTES : nullptr;
         float feat[32];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) { feat[4 * c] = nx[c].x; feat[4 * c + 1] = nx[c].y; feat[4 * c + 2] = nx[c].z; feat[4 * c + 3] = nx[c].w; }
+        for (int c = 0; c < 6; ++c) { feat[4 * c] = nx[c].x; feat[4 * c + 1] = nx[c].y; feat[4 * c + 2] = nx[c].z; feat[4 * c + 3] = nx[c].w; }
+        feat[24] = nf2.x; feat[25] = nf2.y; feat[26] = nf1;
         feat[27] = feat[28] = feat[29] = feat[30] = feat[31] = 0.f;
-        const float dir[3] = {nx[7].x, nx[7].y, nx[7].z};
+        const float dir[3] = {nd2.x, nd2.y, nd1};
         prefetch((long long)tile + gridDim.x);
-        // ---- encoded input A1; this thread: chunks [10 hh, 10 hh + 10)
-        if (hh == 0) {
+        // ---- encoded input A1; this thread: chunks [ec0, ec1)
 #pragma unroll
-            for (int c = 0; c < K1 / 16; ++c) {
-                float v[8];
-                encode_chunk<true>(c, feat, dir, pm, v);
-                store_chunk(a1_hi, a1_lo, TM, c, r, v);
-            }
-        } else {
-#pragma unroll
-            for (int c = K1 / 16; c < K1 / 8; ++c) {
+        for (int c = 0; c < K1 / 8; ++c) {
+            if (c >= ec0 && c < ec1) {
                 float v[8];
                 encode_chunk<true>(c, feat, dir, pm, v);
                 store_chunk(a1_hi, a1_lo, TM, c, r, v);
@@ -115,32 +128,36 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        // Bulk-store bookkeeping (training): groups are committed in the order A1(t), A2(t), A3(t),
+        // A1(t+1), ...; before a buffer is re-written the issuing thread waits until the store that
+        // last read it has drained, and only then signals the MMA barrier every thread waits on.
         if (tid == 0) {
             tc_fence_after();
             issue_gemm_kmajor<SPLIT>(tmem + T_H1, a1_hi, a1_lo, w1_hi, w1_lo, K1, H_, H_);
-            mma_commit(&bar);
             if (SAVE) {
                 bulk_s2g(st + OFF_A1, a1_hi, SZ_A1);
                 bulk_commit();
-                bulk_wait_read2();             // the previous tile's A2 store has left a2_hi
+                bulk_wait_read2();             // A2(t-1) has left a2_hi
             }
+            mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        if (SAVE) __syncthreads();
-        // ---- relu(h1) -> A2 (col 64 = 1 carries b2); columns [32 hh, 32 hh + 32)
+        // ---- relu(h1) -> A2 (col 64 = 1 carries b2); columns [16 hq, 16 hq + 16)
         {
-            float h[32];
-            tmem_ld32(lane_addr + T_H1 + 32 * hh, h);
+            float h[16];
+            tmem_ld16(lane_addr + T_H1 + 16 * hq, h);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(h[c * 8 + i], 0.f);
-                store_chunk(a2_hi, a2_lo, TM, hh * 4 + c, r, v);
+                store_chunk(a2_hi, a2_lo, TM, hq * 2 + c, r, v);
             }
-            const float pad[8] = {hh == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            store_chunk(a2_hi, a2_lo, TM, 8 + hh, r, pad);
+            if (hq < 2) {
+                const float pad[8] = {hq == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                store_chunk(a2_hi, a2_lo, TM, 8 + hq, r, pad);
+            }
         }
         fence_async_smem();
         tc_fence_before();
@@ -148,51 +165,54 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
         if (tid == 0) {
             tc_fence_after();
             issue_gemm_kmajor<SPLIT>(tmem + T_H2, a2_hi, a2_lo, w2_hi, w2_lo, K2, H_, H_);
-            mma_commit(&bar);
             if (SAVE) {
                 bulk_s2g(st + OFF_A2, a2_hi, SZ_A2);
                 bulk_commit();
-                bulk_wait_read2();             // the previous tile's A3 store has left a3_hi
+                bulk_wait_read2();             // A3(t-1) has left a3_hi
             }
+            mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        if (SAVE) __syncthreads();
         // ---- relu(h2) -> layer 3 partial sums (and the A3 tile when saving)
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
         {
-            float h[32];
-            tmem_ld32(lane_addr + T_H2 + 32 * hh, h);
+            float h[16];
+            tmem_ld16(lane_addr + T_H2 + 16 * hq, h);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
                 h[i] = fmaxf(h[i], 0.f);
-                o0 = fmaf(h[i], w3s[hh * 32 + i], o0);
-                o1 = fmaf(h[i], w3s[H_ + hh * 32 + i], o1);
-                o2 = fmaf(h[i], w3s[2 * H_ + hh * 32 + i], o2);
+                o0 = fmaf(h[i], w3s[hq * 16 + i], o0);
+                o1 = fmaf(h[i], w3s[H_ + hq * 16 + i], o1);
+                o2 = fmaf(h[i], w3s[2 * H_ + hq * 16 + i], o2);
             }
             if (SAVE) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) store_chunk(a3_hi, nullptr, TM, hh * 4 + c, r, h + 8 * c);
-                const float pad[8] = {hh == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                store_chunk(a3_hi, nullptr, TM, 8 + hh, r, pad);
+                for (int c = 0; c < 2; ++c) store_chunk(a3_hi, nullptr, TM, hq * 2 + c, r, h + 8 * c);
+                if (hq < 2) {
+                    const float pad[8] = {hq == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    store_chunk(a3_hi, nullptr, TM, 8 + hq, r, pad);
+                }
                 fence_async_smem();
             }
         }
-        if (hh == 1) { part[r][0] = o0; part[r][1] = o1; part[r][2] = o2; }
+        if (hq > 0) { part[pb][hq - 1][r][0] = o0; part[pb][hq - 1][r][1] = o1; part[pb][hq - 1][r][2] = o2; }
+        if (SAVE && tid == 0) bulk_wait_read1();    // A1(t) has left a1_hi: the next tile's encode may overwrite it
         // all tcgen05.ld of this tile are complete (wait::ld) before the next tile's MMAs overwrite TMEM
         tc_fence_before();
         __syncthreads();
-        if (hh == 0 && live) {
-            o0 += part[r][0] + w3s[3 * H_]; o1 += part[r][1] + w3s[3 * H_ + 1]; o2 += part[r][2] + w3s[3 * H_ + 2];
-            __stcs(reinterpret_cast<float4*>(rgb + 4 * (size_t)row),
-                   make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f));
-        }
         if (SAVE && tid == 0) {
             bulk_s2g(st + OFF_A3, a3_hi, SZ_A3);
             bulk_commit();
-            bulk_wait_read2();                 // this tile's A1 store has left a1_hi (next tile's encode goes there)
         }
-        __syncthreads();                       // `part` and a1_hi are free for the next tile
+        if (hq == 0 && live) {
+#pragma unroll
+            for (int k = 0; k < HQ - 1; ++k) { o0 += part[pb][k][r][0]; o1 += part[pb][k][r][1]; o2 += part[pb][k][r][2]; }
+            o0 += w3s[3 * H_]; o1 += w3s[3 * H_ + 1]; o2 += w3s[3 * H_ + 2];
+            __stcs(reinterpret_cast<float4*>(rgb + 4 * (size_t)row),
+                   make_float4(1.f / (1.f + expf(-o0)), 1.f / (1.f + expf(-o1)), 1.f / (1.f + expf(-o2)), 0.f));
+        }
+        pb ^= 1;                               // `part` is double-buffered: no barrier at the end of the tile
     }
     if (SAVE && tid == 0) bulk_wait0();
     tc_fence_before();

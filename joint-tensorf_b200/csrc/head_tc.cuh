@@ -53,23 +53,25 @@ __device__ inline void stage_weight(unsigned char* hi, unsigned char* lo, const 
 }
 
 // issue the k-steps of one GEMM: D[128 x N] = A[128 x K] * B[N x K]^T, both K-major tiles.
+// The descriptors of k-step ks differ from those of step 0 only in the start-address field
+// (+ 2 chunks), so they are one 64-bit add each: the issuing thread's chain stays short.
 template <int SPLIT>
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, const unsigned char* a_hi, const unsigned char* a_lo,
                                                   const unsigned char* b_hi, const unsigned char* b_lo, int K, int NR,
                                                   int N) {
     const uint32_t idesc = idesc_bf16(128, N, 0, 0);
     const uint32_t a_lbo = TM * 16, b_lbo = NR * 16;
-    uint32_t acc = 0;
+    const uint64_t ah0 = smem_desc(smem_u32(a_hi), a_lbo, 128), bh0 = smem_desc(smem_u32(b_hi), b_lbo, 128);
+    const uint64_t al0 = SPLIT == 2 ? smem_desc(smem_u32(a_lo), a_lbo, 128) : 0;
+    const uint64_t bl0 = SPLIT == 2 ? smem_desc(smem_u32(b_lo), b_lbo, 128) : 0;
+    const uint64_t a_inc = (2 * a_lbo) >> 4, b_inc = (2 * b_lbo) >> 4;
+#pragma unroll 5
     for (int ks = 0; ks < K / 16; ++ks) {
-        const uint64_t ah = smem_desc(smem_u32(a_hi) + ks * 2 * a_lbo, a_lbo, 128);
-        const uint64_t bh = smem_desc(smem_u32(b_hi) + ks * 2 * b_lbo, b_lbo, 128);
-        mma_bf16(d_tmem, ah, bh, idesc, acc);
-        acc = 1;
+        const uint64_t ah = ah0 + ks * a_inc, bh = bh0 + ks * b_inc;
+        mma_bf16(d_tmem, ah, bh, idesc, ks > 0 ? 1u : 0u);
         if (SPLIT == 2) {
-            const uint64_t al = smem_desc(smem_u32(a_lo) + ks * 2 * a_lbo, a_lbo, 128);
-            const uint64_t bl = smem_desc(smem_u32(b_lo) + ks * 2 * b_lbo, b_lbo, 128);
-            mma_bf16(d_tmem, ah, bl, idesc, 1);
-            mma_bf16(d_tmem, al, bh, idesc, 1);
+            mma_bf16(d_tmem, ah, bl0 + ks * b_inc, idesc, 1);
+            mma_bf16(d_tmem, al0 + ks * a_inc, bh, idesc, 1);
         }
     }
 }

@@ -135,18 +135,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // residual of the bf16 rounding (second term of the 2-term split a = hi + lo)
 __device__ __forceinline__ float bf16_resid(float a) { return a - __bfloat162float(__float2bfloat16_rn(a)); }
 
+// hi/lo split of a float pair with packed conversions only: hi = bf16x2(a, b) (one F2FP), the
+// exact fp32 value of each half is a shift / mask of the packed word, lo = bf16x2 of the residuals.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16(a, b);
+    lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+}
+
 // store 8 consecutive columns (one 16 B chunk) of row `r` of an R-row tile; lo != nullptr
 // additionally stores the rounding residuals into the second-term tile.
 __device__ __forceinline__ void store_chunk(unsigned char* hi, unsigned char* lo, int R, int chunk, int r, const float v[8]) {
-    uint4 h;
-    h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]); h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(hi + (size_t)chunk * R * 16 + r * 16) = h;
+    uint4 h, l;
     if (lo) {
-        uint4 l;
-        l.x = pack_bf16(bf16_resid(v[0]), bf16_resid(v[1])); l.y = pack_bf16(bf16_resid(v[2]), bf16_resid(v[3]));
-        l.z = pack_bf16(bf16_resid(v[4]), bf16_resid(v[5])); l.w = pack_bf16(bf16_resid(v[6]), bf16_resid(v[7]));
+        split_pair(v[0], v[1], h.x, l.x); split_pair(v[2], v[3], h.y, l.y);
+        split_pair(v[4], v[5], h.z, l.z); split_pair(v[6], v[7], h.w, l.w);
         *reinterpret_cast<uint4*>(lo + (size_t)chunk * R * 16 + r * 16) = l;
+    } else {
+        h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]); h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
     }
+    *reinterpret_cast<uint4*>(hi + (size_t)chunk * R * 16 + r * 16) = h;
 }
 
 }  // namespace tc

@@ -258,16 +258,19 @@ def own_arm(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # > 126 MB L2
 
     def timed(fn, k):
-        tot = 0.0
+        """Sum of the K per-step device times (CUDA events on the launching stream). The L2
+        flush between steps is on the stream but outside every event pair; the host does not
+        synchronise inside the loop, so it queues launches ahead as a training loop does."""
+        evs = []
         for _ in range(k):
             flush.fill_(1.0)                                           # evict L2 between steps (untimed)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             fn()
             e.record()
-            e.synchronize()
-            tot += s.elapsed_time(e)
-        return tot
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
 
     def barrier():
         torch.cuda.synchronize()

@@ -98,10 +98,11 @@ int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_facto
  *   d_o[r] += sum_j dL/du_j * inv,   d_d[r] += sum_j dL/du_j * inv * t_j     (ray r = sidx/S)
  * i.e. the autograd of rays_pts = o + d*t and normalize_coord (tensorBase.py:502-503,597).
  * The element list must be ray-major (as jt_march_compact / jt_alpha_fwd produce it).
- * d_o / d_d [N][3] must be initialised by the caller (zeros, or jt_ray_init for NDC rays). */
+ * d_o / d_d [N][3] must be initialised by the caller (zeros, or jt_ray_init for NDC rays).
+ * gin_bf16 = 1 (app only): gin rows are bf16 [n][sum C] as jt_head_bwd_tc writes them. */
 int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,
                        const float* samp, const int* slot, const int* sidx, const int* n_dev, int n_max,
-                       const float* gin, int n_samples, const float* h_inv, float* d_o, float* d_d,
+                       const void* gin, int gin_bf16, int n_samples, const float* h_inv, float* d_o, float* d_d,
                        cudaStream_t stream);
 /* d_o = 0; d_d = dnorm_r / |d|^2 * d  (NDC rays: dists are scaled by |ray_dir|, batBase.py:63-65;
  * dnorm holds dL/d|d| * |d| from jt_render_bwd) or 0 when dnorm is NULL. */
@@ -172,7 +173,7 @@ int jt_head_mlp_fwd_tc(int split, const float* featdir, const float* W1, const f
  * the weight gradients into gWb [27][144], gW1 [64][150], gb1, gW2 [64][64], gb2, gW3 [3][64],
  * gb3. relu masks are the forward's own; nothing is recomputed. */
 int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, const float* Wb, const float* W1, const float* W2,
-                   const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps, void* stage,
+                   const float* W3, const int* n_dev, int n_max, float fea_progress, void* dcomps, int dcomps_bf16, void* stage,
                    float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                    cudaStream_t stream);
 

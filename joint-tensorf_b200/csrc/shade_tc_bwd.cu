@@ -53,10 +53,11 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint4 q) {
 
 constexpr int NTB = 2 * TM;     // two threads per sample row (column halves), as in the forward kernel
 
-__global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
+template <bool DC16>
+__global__ void __launch_bounds__(NTB, 2) head_bwd_data_kernel(
     const float* __restrict__ dout, const float* __restrict__ feat_in, int ldf, const float* __restrict__ Wb,
     const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
-    const int* __restrict__ n_dev, int n_fixed, float fprog, float* __restrict__ dcomps,
+    const int* __restrict__ n_dev, int n_fixed, float fprog, void* __restrict__ dcomps_out,
     unsigned char* __restrict__ stage) {
     using L = BwdSmem;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -87,33 +88,41 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
     uint32_t phase = 0;
     const float pf0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f), pf1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
 
+    // the global reads of the NEXT tile (relu-mask chunks of A3 / A2, the feature row, dout) are
+    // issued while the current tile computes
+    float go[3];
+    uint4 q3[4], q2[4];
+    float feat[16];
+    auto prefetch = [&](long long t) {
+        const long long rw = t * TM + r;
+        const bool lv = rw < n;
+        const bool tv = t * TM < n;
+        const unsigned char* stn = stage + (size_t)(tv ? t : 0) * STAGE_TILE_BYTES;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const size_t o = (size_t)(hh * 4 + c4) * TM * 16 + r * 16;
+            q3[c4] = tv ? __ldg(reinterpret_cast<const uint4*>(stn + OFF_A3 + o)) : make_uint4(0, 0, 0, 0);
+            q2[c4] = tv ? __ldg(reinterpret_cast<const uint4*>(stn + OFF_A2 + o)) : make_uint4(0, 0, 0, 0);
+        }
+        const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(lv ? rw : 0) * ldf) + 4 * hh;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lv && (hh == 0 || q < 3)) f4 = __ldg(fp + q);
+            feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
+        }
+        go[0] = go[1] = go[2] = 0.f;
+        if (lv) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(dout) + rw);
+            go[0] = g4.x; go[1] = g4.y; go[2] = g4.z;
+        }
+    };
+    prefetch(blockIdx.x);
+
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
         const int row = tile * TM + r;
         const bool live = row < n;
         unsigned char* st = stage + (size_t)tile * STAGE_TILE_BYTES;
-        // ---- all global reads of the tile are issued up front (independent loads in flight together)
-        float go[3] = {0.f, 0.f, 0.f};
-        uint4 q3[4], q2[4];
-        float feat[16];
-        {
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const size_t o = (size_t)(hh * 4 + c4) * TM * 16 + r * 16;
-                q3[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A3 + o));
-                q2[c4] = __ldg(reinterpret_cast<const uint4*>(st + OFF_A2 + o));
-            }
-            const float4* fp = reinterpret_cast<const float4*>(feat_in + (size_t)(live ? row : 0) * ldf) + 4 * hh;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live && (hh == 0 || q < 3)) f4 = __ldg(fp + q);
-                feat[4 * q] = f4.x; feat[4 * q + 1] = f4.y; feat[4 * q + 2] = f4.z; feat[4 * q + 3] = f4.w;
-            }
-            if (live) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(dout) + row);
-                go[0] = g4.x; go[1] = g4.y; go[2] = g4.z;
-            }
-        }
         // ---- S0: dh2 = (dout W3) . [h2 > 0] -> D2 (this thread: columns [32 hh, 32 hh + 32)) ; dout -> DO
         if (hh == 0) {
             const float v[8] = {go[0], go[1], go[2], 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
                     const int el = 8 * k + q;
                     if (16 * hh + el < F_) {
                         float sn, co;
-                        sincosf(feat[el], &sn, &co);
+                        fast_sincos(feat[el], &sn, &co);
                         const float s2 = 2.f * sn * co, c2 = 1.f - 2.f * sn * sn;
                         df[el] += pf0 * (co * g[4 * q] - sn * g[4 * q + 2]) + 2.f * pf1 * (c2 * g[4 * q + 1] - s2 * g[4 * q + 3]);
                     }
@@ -194,6 +203,7 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
             store_chunk(DF, nullptr, TM, 2 * hh, r, df);
             store_chunk(DF, nullptr, TM, 2 * hh + 1, r, df + 8);
         }
+        prefetch((long long)tile + gridDim.x);   // q3 / q2 / feat / go of this tile are dead from here on
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -206,25 +216,42 @@ __global__ void __launch_bounds__(NTB) head_bwd_data_kernel(
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- S3: dcomps row -> global (fp32); hh = 0: columns [0,64) + [128,144), hh = 1: [64,128)
+        // ---- S3: dcomps row -> global (fp32, or bf16 when DC16); hh = 0: columns [0,64) + [128,144), hh = 1: [64,128)
         {
-            float4* dst = reinterpret_cast<float4*>(dcomps + (size_t)(live ? row : 0) * CT);
+            float* dstf = reinterpret_cast<float*>(dcomps_out) + (size_t)(live ? row : 0) * CT;
+            uint4* dsth = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dcomps_out) + (size_t)(live ? row : 0) * CT);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 float g[32];
                 const int c0 = 64 * hh + 32 * k;
                 tmem_ld32(lane_addr + T_DC + c0, g);
                 if (live) {
+                    if (DC16) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) __stcs(dst + c0 / 4 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+                        for (int q = 0; q < 4; ++q)
+                            __stcs(dsth + c0 / 8 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                                                 pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            __stcs(reinterpret_cast<float4*>(dstf) + c0 / 4 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+                    }
                 }
             }
             if (hh == 0) {
                 float g[16];
                 tmem_ld16(lane_addr + T_DC + 128, g);
                 if (live) {
+                    if (DC16) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) __stcs(dst + 32 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+                        for (int q = 0; q < 2; ++q)
+                            __stcs(dsth + 16 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                                             pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            __stcs(reinterpret_cast<float4*>(dstf) + 32 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+                    }
                 }
             }
         }
@@ -359,8 +386,8 @@ extern "C" long long jt_head_tc_stage_bytes(int n_max) {
 }
 
 extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, const float* Wb, const float* W1, const float* W2,
-                              const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps,
-                              void* stage, float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
+                              const float* W3, const int* n_dev, int n_max, float fea_progress, void* dcomps,
+                              int dcomps_bf16, void* stage, float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3,
                               float* gb3, cudaStream_t stream) {
     JT_CHECK_ARG(dout && feat && Wb && W1 && W2 && W3 && dcomps && stage && ldf >= 28 && ldf % 4 == 0);
     JT_CHECK_ARG(gWb && gW1 && gb1 && gW2 && gb2 && gW3 && gb3);
@@ -369,11 +396,16 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
     long long tiles = ((long long)n_max + TM - 1) / TM;
     int grid_d = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
     int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    if (int rc = set_smem(head_bwd_data_kernel, BwdSmem::total)) return rc;
+    if (int rc = set_smem(head_bwd_data_kernel<false>, BwdSmem::total)) return rc;
+    if (int rc = set_smem(head_bwd_data_kernel<true>, BwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_wgrad_kernel, WG_STAGES * WG_STAGE_BYTES)) return rc;
     g_launches += 2;
-    head_bwd_data_kernel<<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max, fea_progress,
-                                                                 dcomps, static_cast<unsigned char*>(stage));
+    if (dcomps_bf16)
+        head_bwd_data_kernel<true><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
+                                                                           fea_progress, dcomps, static_cast<unsigned char*>(stage));
+    else
+        head_bwd_data_kernel<false><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
+                                                                            fea_progress, dcomps, static_cast<unsigned char*>(stage));
     head_bwd_wgrad_kernel<<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(static_cast<const unsigned char*>(stage),
                                                                               n_dev, n_max, gWb, gW1, gb1, gW2, gb2,
                                                                               gW3, gb3);

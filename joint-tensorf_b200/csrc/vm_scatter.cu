@@ -53,7 +53,8 @@ struct ScatterArgs {
     const int* sidx;        // [V] ray * S + k
     const int* n_dev;
     int n_fixed;
-    const float* gin;       // APP: [n][ctot]; density: [n]
+    const float* gin;       // APP: [n][ctot] (fp32, or bf16 when gin_bf16); density: [n]
+    int gin_bf16;
     float* d_o;             // [N][3], accumulated
     float* d_d;             // [N][3], accumulated
     float inv[3];           // 2 / aabbSize (normalize_coord)
@@ -70,7 +71,7 @@ struct ScatterArgs {
 // REDs); only the gradient accumulators live across steps.
 struct RaySums { float o[3], d[3]; };      // per axis: sum_j dL/du_j, sum_j dL/du_j * t_j (this lane's channels)
 
-template <bool APP, int NQ, int I>
+template <bool APP, int NQ, int I, bool GB16>
 __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
                                            int& ray, int& ray_end, RaySums& rs) {
     const Factors& F = A.F;
@@ -166,8 +167,17 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
             const float4 a = ldg4(P + o00 + k * qs), b = ldg4(P + o10 + k * qs);
             const float4 c = ldg4(P + o01 + k * qs), d = ldg4(P + o11 + k * qs);
             const float4 la = ldg4(Ln + ol0 + k * qs), lb = ldg4(Ln + ol1 + k * qs);
-            const float4 g4 = APP ? __ldcs(reinterpret_cast<const float4*>(gbase + (size_t)e * F.ctot + k * qs))
-                                  : make_float4(gs, gs, gs, gs);
+            float4 g4;
+            if (APP && GB16) {                       // bf16 row of the tensor-core head's dcomps
+                const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(
+                    reinterpret_cast<const unsigned short*>(A.gin) + (size_t)e * F.ctot + F.off[I] + q + k * qs));
+                g4 = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+            } else if (APP) {
+                g4 = __ldcs(reinterpret_cast<const float4*>(gbase + (size_t)e * F.ctot + k * qs));
+            } else {
+                g4 = make_float4(gs, gs, gs, gs);
+            }
             float4 pv, lv;
             pv.x = a.x * w00 + b.x * w10 + c.x * w01 + d.x * w11; pv.y = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
             pv.z = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11; pv.w = a.w * w00 + b.w * w10 + c.w * w01 + d.w * w11;
@@ -203,7 +213,7 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
     flush_ray();
 }
 
-template <bool APP, int NQ, int MINB>
+template <bool APP, int NQ, int MINB, bool GB16>
 __global__ void __launch_bounds__(128, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
     const int LW = NQ > 1 ? 4 : LW_rt;                   // multi-quad lanes: 4 lanes per walker, compile-time strides
     const int n = A.n_dev ? *A.n_dev : A.n_fixed;
@@ -220,9 +230,9 @@ __global__ void __launch_bounds__(128, MINB) vm_scatter_walk_kernel(const Scatte
         RaySums rs;
 #pragma unroll
         for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
-        walk_plane<APP, NQ, 0>(A, e0, e1, q, qs, ray, ray_end, rs);
-        walk_plane<APP, NQ, 1>(A, e0, e1, q, qs, ray, ray_end, rs);
-        walk_plane<APP, NQ, 2>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 0, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 1, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 2, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
     }
 }
 
@@ -232,7 +242,7 @@ using namespace jt;
 
 extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads,
                                   const int* h_dims, const float* samp, const int* slot, const int* sidx,
-                                  const int* n_dev, int n_max, const float* gin, int n_samples, const float* h_inv,
+                                  const int* n_dev, int n_max, const void* gin, int gin_bf16, int n_samples, const float* h_inv,
                                   float* d_o, float* d_d, cudaStream_t stream) {
     JT_CHECK_ARG(h_factors && h_factor_grads && h_dims && samp && sidx && gin && h_inv && d_o && d_d && n_samples > 0);
     if (n_max <= 0) return JT_OK;
@@ -248,7 +258,8 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     }
     JT_CHECK_ARG((long long)n_max < 2147483647LL);
     A.samp = reinterpret_cast<const float4*>(samp);
-    A.slot = slot; A.sidx = sidx; A.n_dev = n_dev; A.n_fixed = n_max; A.gin = gin;
+    A.slot = slot; A.sidx = sidx; A.n_dev = n_dev; A.n_fixed = n_max; A.gin = static_cast<const float*>(gin); A.gin_bf16 = gin_bf16;
+    JT_CHECK_ARG(!gin_bf16 || app);
     A.d_o = d_o; A.d_d = d_d;
     for (int a = 0; a < 3; ++a) A.inv[a] = h_inv[a];
     A.S = n_samples;
@@ -256,8 +267,6 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     // lanes per walker / quads per lane: uniform C in {16, 32, 48} -> 4 lanes x C/16 quads, else one quad per lane
     int nq = 1, LW = cmax / 4;
     if (A.F.C[0] == A.F.C[1] && A.F.C[1] == A.F.C[2] && cmax % 16 == 0 && cmax <= 48) { nq = cmax / 16; LW = 4; }
-    static const char* env_mode0 = getenv("JT_SC_MODE");
-    if (env_mode0 && atoi(env_mode0) == 1 && nq > 1) { nq = 1; LW = cmax / 4; }
     JT_CHECK_ARG(LW >= 1 && LW <= 128);
     const int wpc = 128 / LW;                                 // walkers per CTA
     const int threads = ((wpc * LW + 31) / 32) * 32;
@@ -266,12 +275,10 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     long long cap = (long long)kNumSMs * 32;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
-    static const char* env_mode = getenv("JT_SC_MODE");       // tuning: 1 = one quad per lane, 2 = 3 quads at 168 regs
-    const int mode = env_mode ? atoi(env_mode) : 0;
-    if (mode == 1 && nq > 1) { nq = 1; LW = cmax / 4; }
-#define JT_SC(APPV, NQV, MB) vm_scatter_walk_kernel<APPV, NQV, MB><<<grid, threads, 0, stream>>>(A, LW, wpc)
-    if (app) { if (nq == 3 && mode == 2) JT_SC(true, 3, 3); else if (nq == 3) JT_SC(true, 3, 2); else if (nq == 2) JT_SC(true, 2, 3); else JT_SC(true, 1, 3); }
-    else { if (nq == 3 && mode == 2) JT_SC(false, 3, 3); else if (nq == 3) JT_SC(false, 3, 2); else if (nq == 2) JT_SC(false, 2, 3); else JT_SC(false, 1, 3); }
+#define JT_SC(APPV, NQV, MB, GB) vm_scatter_walk_kernel<APPV, NQV, MB, GB><<<grid, threads, 0, stream>>>(A, LW, wpc)
+    if (app && gin_bf16) { if (nq == 3) JT_SC(true, 3, 2, true); else if (nq == 2) JT_SC(true, 2, 3, true); else JT_SC(true, 1, 3, true); }
+    else if (app) { if (nq == 3) JT_SC(true, 3, 2, false); else if (nq == 2) JT_SC(true, 2, 3, false); else JT_SC(true, 1, 3, false); }
+    else { if (nq == 3) JT_SC(false, 3, 2, false); else if (nq == 2) JT_SC(false, 2, 3, false); else JT_SC(false, 1, 3, false); }
 #undef JT_SC
     JT_RETURN_LAUNCH();
 }

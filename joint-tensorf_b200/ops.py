@@ -164,8 +164,8 @@ def vm_scatter_rays(app, fs, gp, gl, samp, slot, sidx, n_dev, n_max, gin, n_samp
     gptrs = ptrs([g.data_ptr() for g in gp] + [g.data_ptr() for g in gl])
     with TIMER.span("vm_app_bwd" if app else "vm_density_bwd"):
         check(_lib.lib().jt_vm_scatter_rays(int(app), fs.ptrs, gptrs, fs.dims, _p(samp), _p(slot), _p(sidx),
-                                            _p(n_dev), int(n_max), _p(gin), int(n_samples), h_inv, _p(d_o), _p(d_d),
-                                            _stream()), "jt_vm_scatter_rays")
+                                            _p(n_dev), int(n_max), _p(gin), int(gin.dtype == torch.bfloat16),
+                                            int(n_samples), h_inv, _p(d_o), _p(d_d), _stream()), "jt_vm_scatter_rays")
 
 
 # ------------------------------------------------------------------ K3
@@ -244,7 +244,8 @@ def head_bwd_tc(dout, feat, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, 
     feat: [A][ldf] rows whose first 27 floats are the basis projection (ldf = 28 or 32)."""
     with TIMER.span("head_bwd_tc"):
         check(_lib.lib().jt_head_bwd_tc(_p(dout), _p(feat), int(feat.shape[1]), _p(wb), _p(w1), _p(w2), _p(w3), _p(n_dev), int(n_max),
-                                        float(fprog), _p(dcomps), _p(stage), *[_p(g) for g in grads], _stream()),
+                                        float(fprog), _p(dcomps), int(dcomps.dtype == torch.bfloat16), _p(stage),
+                                        *[_p(g) for g in grads], _stream()),
               "jt_head_bwd_tc")
 
 

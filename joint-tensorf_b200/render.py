@@ -263,7 +263,8 @@ class VMRender(torch.autograd.Function):
                             cfg.h_inv, d_o, d_d)
 
         g_basis = torch.zeros_like(b["basis_w"])
-        dcomps = torch.empty((cap, afs.ctot), device=dev)
+        # tensor-core head: dcomps crosses HBM as bf16 (its GEMM operands are bf16 already)
+        dcomps = torch.empty((cap, afs.ctot), device=dev, dtype=torch.bfloat16 if cfg.head == "tc" else torch.float32)
         if cfg.head == "tc":
             w1, b1, w2, b2, w3, b3 = b["head"]
             head_grads = [torch.zeros_like(t) for t in b["head"]]

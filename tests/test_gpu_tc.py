@@ -70,8 +70,9 @@ def test_head_fwd_tc_matches_fp32(split, tol, a_count):
     assert (rgb[:, :3].cpu() - ref).abs().max() <= tol
 
 
+@pytest.mark.parametrize("dc_dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("a_count", [1, 128, 1000, 40000])
-def test_head_bwd_tc_matches_fp32_autograd(a_count):
+def test_head_bwd_tc_matches_fp32_autograd(a_count, dc_dtype):
     p, comps, rays_d, sidx, aidx, S = _head_inputs(a_count, seed=3)
     g = torch.Generator().manual_seed(7)
     dout = torch.randn(a_count, 3, generator=g) * 0.1
@@ -90,7 +91,7 @@ def test_head_bwd_tc_matches_fp32_autograd(a_count):
     d = {k: v.to(DEV).contiguous() for k, v in p.items()}
     dout4 = torch.zeros((a_count, 4), device=DEV)
     dout4[:, :3] = dout.to(DEV)
-    dcomps = torch.zeros((a_count, 144), device=DEV)
+    dcomps = torch.zeros((a_count, 144), device=DEV, dtype=dc_dtype)
     grads = [torch.zeros_like(d[k]) for k in names]
     cnt = torch.tensor([a_count], device=DEV, dtype=torch.int32)
     rgb = torch.zeros((a_count, 4), device=DEV)
@@ -105,6 +106,7 @@ def test_head_bwd_tc_matches_fp32_autograd(a_count):
         return float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
     # per-sample rows: a relu unit whose fp32 pre-activation is within rounding of 0 may take the other
     # branch (a tie, ~1e-6 of all units) -- allow <= 0.02 % such rows, bound everything else by 2e-2
+    dcomps = dcomps.float()
     err_rows = (dcomps.cpu().double() - cr.grad.double()).abs().amax(1) / cr.grad.double().abs().max()
     assert float((err_rows > 2e-2).double().mean()) <= 2e-4, float((err_rows > 2e-2).double().mean())
     assert float(torch.linalg.norm(dcomps.cpu().double() - cr.grad.double()) / torch.linalg.norm(cr.grad.double())) <= 2e-2

@@ -66,14 +66,36 @@ struct ScatterArgs {
 // (C = 4 LW NQ), i.e. per tap the walker's lanes read LW x 16 contiguous bytes NQ times.
 // Work unit = a segment of `seg` consecutive elements; the walker walks it once per plane
 // (plane index is a compile-time constant of walk_plane). Walkers are laid out over the
-// CTA's threads contiguously and use no warp-level collectives. The tap values are re-read
-// every step (L1 hits while the cell is unchanged: loads are ~5x cheaper per lane than
-// REDs); only the gradient accumulators live across steps.
+// CTA's threads contiguously and use no warp-level collectives.
+//
+// Tap staging: the kernel is latency-bound, not RED-bound, once the REDs are merged, and the
+// accumulators leave no registers to keep loads in flight. So each lane owns a private,
+// double-buffered shared-memory slot set for the taps of its quads: when the look-ahead
+// (one step) sees that the next sample enters another plane / line cell, the lane issues
+// cp.async copies of the new cell's taps into the idle buffer while the current step
+// computes out of the active one. A lane only ever reads what it copied itself, so no
+// barrier is needed -- cp.async.wait_group orders it.
 struct RaySums { float o[3], d[3]; };      // per axis: sum_j dL/du_j, sum_j dL/du_j * t_j (this lane's channels)
+
+constexpr int SC_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct StepPos {          // tap position of one sample on one plane/line pair
+    int x0, y0, l0;       // unclamped cell indices (NaN -> -2: both taps out of range)
+    float fx, fy, fl;     // fractions
+    float t;              // depth along the ray
+    int sid;              // ray * S + k
+};
 
 template <bool APP, int NQ, int I, bool GB16>
 __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
-                                           int& ray, int& ray_end, RaySums& rs) {
+                                           int& ray, int& ray_end, RaySums& rs, float4* __restrict__ sm) {
     const Factors& F = A.F;
     constexpr int ax = I == 2 ? 1 : 0, ay = I == 0 ? 1 : 2, al = 2 - I;      // matMode / vecMode (tensorBase.py:405-406)
     const int W = F.W[I], H = F.H[I], L = F.L[I], C = F.C[I];
@@ -82,8 +104,68 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
     const float* __restrict__ Ln = F.line[I] + q;
     float* __restrict__ GP = A.G.plane[I] + q;
     float* __restrict__ GL = A.G.line[I] + q;
-    const float* __restrict__ gbase = APP ? A.gin + F.off[I] + q : A.gin;
     const float sclx = 0.5f * (float)(W - 1), scly = 0.5f * (float)(H - 1), scll = 0.5f * (float)(L - 1);
+    // this lane's staging slots (float4 index = slot * SC_THREADS): plane buffer b, tap c, quad k -> (b*4 + c)*NQ + k;
+    // line buffer b, tap c, quad k -> 8 NQ + (b*2 + c)*NQ + k
+    auto pslot = [&](int b, int c, int k) -> float4* { return sm + ((b * 4 + c) * NQ + k) * SC_THREADS; };
+    auto lslot = [&](int b, int c, int k) -> float4* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * SC_THREADS; };
+
+    auto make_pos = [&](const float4 u4, const int sid) {
+        const float u[3] = {u4.x, u4.y, u4.z};
+        StepPos p;
+        const float fxp = (u[ax] + 1.0f) * sclx, fyp = (u[ay] + 1.0f) * scly, flp = (u[al] + 1.0f) * scll;
+        const float xf = floorf(fxp), yf = floorf(fyp), lf = floorf(flp);
+        p.x0 = (int)fminf(fmaxf(xf, -2.0f), (float)W); p.y0 = (int)fminf(fmaxf(yf, -2.0f), (float)H);
+        p.l0 = (int)fminf(fmaxf(lf, -2.0f), (float)L);
+        p.fx = fxp - xf; p.fy = fyp - yf; p.fl = flp - lf;
+        p.t = u4.w; p.sid = sid;
+        return p;
+    };
+    // clamped element offsets of the 4 plane corners / 2 line taps of a cell
+    auto plane_offs = [&](int x0, int y0, unsigned o[4]) {
+        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+        o[0] = (unsigned)((yc0 * W + xc0) * C); o[1] = (unsigned)((yc0 * W + xc1) * C);
+        o[2] = (unsigned)((yc1 * W + xc0) * C); o[3] = (unsigned)((yc1 * W + xc1) * C);
+    };
+    auto line_offs = [&](int l0, unsigned o[2]) {
+        o[0] = (unsigned)(min(max(l0, 0), L - 1) * C); o[1] = (unsigned)(min(max(l0 + 1, 0), L - 1) * C);
+    };
+    auto fetch_plane = [&](int b, const unsigned o[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) cp_async16(pslot(b, c, k), P + o[c] + k * qs);
+    };
+    auto fetch_line = [&](int b, const unsigned o[2]) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) cp_async16(lslot(b, c, k), Ln + o[c] + k * qs);
+    };
+    // upstream gradient of element e for this lane's quads: fetched raw one step ahead (the
+    // conversion happens at use, so the load latency stays off the issue path)
+    struct GinRaw { float4 f; uint2 h; float s; };
+    auto load_gin = [&](int e, GinRaw g[NQ]) {
+        if (APP && GB16) {                       // bf16 row of the tensor-core head's dcomps
+            const unsigned short* row = reinterpret_cast<const unsigned short*>(A.gin) + (size_t)e * F.ctot + F.off[I] + q;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) g[k].h = __ldcs(reinterpret_cast<const uint2*>(row + k * qs));
+        } else if (APP) {
+            const float* row = A.gin + (size_t)e * F.ctot + F.off[I] + q;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) g[k].f = __ldcs(reinterpret_cast<const float4*>(row + k * qs));
+        } else {
+            g[0].s = A.gin[e];
+        }
+    };
+    auto gin_value = [&](const GinRaw g[NQ], int k) -> float4 {
+        if (APP && GB16)
+            return make_float4(__uint_as_float(g[k].h.x << 16), __uint_as_float(g[k].h.x & 0xFFFF0000u),
+                               __uint_as_float(g[k].h.y << 16), __uint_as_float(g[k].h.y & 0xFFFF0000u));
+        if (APP) return g[k].f;
+        return make_float4(g[0].s, g[0].s, g[0].s, g[0].s);
+    };
 
     // accumulated cell: indices and clamped element offsets
     int cx = INT_MIN, cy = INT_MIN, cl = INT_MIN;
@@ -104,37 +186,72 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
         for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
     };
 
-    // software pipeline: the sample record of element e+1 is fetched while e is processed
-    int jn = A.slot ? A.slot[e0] : e0;
-    float4 un = A.samp[jn];
-    int sn = A.sidx[jn];
+    // ---- prologue: position + taps of element e0, record of e0 + 1, upstream gradient of e0
+    StepPos pn;
+    unsigned on[4], oln[2];          // offsets of the cell whose taps sit in the "next" buffers
+    int pbn = 0, lbn = 0;
+    {
+        const int j0 = A.slot ? A.slot[e0] : e0;
+        pn = make_pos(A.samp[j0], A.sidx[j0]);
+        plane_offs(pn.x0, pn.y0, on);
+        line_offs(pn.l0, oln);
+        fetch_plane(0, on);
+        fetch_line(0, oln);
+        cp_async_commit();
+    }
+    // sample records are fetched two steps ahead and their slot indices three steps ahead, so that no
+    // load waits on the result of another load issued in the same step
+    auto slot_of = [&](int e) -> int { return e < e1 ? (A.slot ? A.slot[e] : e) : 0; };
+    float4 un = f4z();
+    int sn = 0;
+    if (e0 + 1 < e1) {
+        const int j1 = slot_of(e0 + 1);
+        un = A.samp[j1];
+        sn = A.sidx[j1];
+    }
+    int jn2 = slot_of(e0 + 2);
+    GinRaw gn[NQ];
+    load_gin(e0, gn);
+
     for (int e = e0; e < e1; ++e) {
-        const float4 u4 = un;
-        const int sid = sn;
+        const StepPos pc = pn;
+        const int pb = pbn, lb = lbn;
+        const unsigned o00 = on[0], o10 = on[1], o01 = on[2], o11 = on[3], ol0 = oln[0], ol1 = oln[1];
+        GinRaw gc[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) gc[k] = gn[k];
+        // ---- look-ahead: position of e+1; its taps are copied into the idle buffers if it enters a new cell
         if (e + 1 < e1) {
-            jn = A.slot ? A.slot[e + 1] : e + 1;
-            un = A.samp[jn];
-            sn = A.sidx[jn];
+            pn = make_pos(un, sn);
+            if (pn.x0 != pc.x0 || pn.y0 != pc.y0) {
+                plane_offs(pn.x0, pn.y0, on);
+                pbn = pb ^ 1;
+                fetch_plane(pbn, on);
+            }
+            if (pn.l0 != pc.l0) {
+                line_offs(pn.l0, oln);
+                lbn = lb ^ 1;
+                fetch_line(lbn, oln);
+            }
+            load_gin(e + 1, gn);
+            if (e + 2 < e1) {
+                un = A.samp[jn2];
+                sn = A.sidx[jn2];
+            }
+            jn2 = slot_of(e + 3);
         }
-        const float u[3] = {u4.x, u4.y, u4.z};
-        if (sid >= ray_end || sid < ray_end - A.S) {          // another ray (lists are ray-major)
+        cp_async_commit();
+        cp_async_wait1();                                    // everything but the look-ahead copies has landed
+
+        if (pc.sid >= ray_end || pc.sid < ray_end - A.S) {   // another ray (lists are ray-major)
             flush_ray();
-            ray = sid / A.S;
+            ray = pc.sid / A.S;
             ray_end = (ray + 1) * A.S;
         }
-        // tap positions (ATen grid_sampler, align_corners=True, zeros padding)
-        const float fxp = (u[ax] + 1.0f) * sclx, fyp = (u[ay] + 1.0f) * scly, flp = (u[al] + 1.0f) * scll;
-        const float xf = floorf(fxp), yf = floorf(fyp), lf = floorf(flp);
-        const int x0 = (int)fminf(fmaxf(xf, -2.0f), (float)W), y0 = (int)fminf(fmaxf(yf, -2.0f), (float)H),
-                  l0 = (int)fminf(fmaxf(lf, -2.0f), (float)L);        // NaN -> -2: both taps out of range
+        const int x0 = pc.x0, y0 = pc.y0, l0 = pc.l0;
         const float mx0 = (x0 >= 0 && x0 < W) ? 1.f : 0.f, mx1 = (x0 + 1 >= 0 && x0 + 1 < W) ? 1.f : 0.f;
         const float my0 = (y0 >= 0 && y0 < H) ? 1.f : 0.f, my1 = (y0 + 1 >= 0 && y0 + 1 < H) ? 1.f : 0.f;
         const float ml0 = (l0 >= 0 && l0 < L) ? 1.f : 0.f, ml1 = (l0 + 1 >= 0 && l0 + 1 < L) ? 1.f : 0.f;
-        const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
-        const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
-        const unsigned o00 = (unsigned)((yc0 * W + xc0) * C), o10 = (unsigned)((yc0 * W + xc1) * C);
-        const unsigned o01 = (unsigned)((yc1 * W + xc0) * C), o11 = (unsigned)((yc1 * W + xc1) * C);
-        const unsigned ol0 = (unsigned)(min(max(l0, 0), L - 1) * C), ol1 = (unsigned)(min(max(l0 + 1, 0), L - 1) * C);
         if (x0 != cx || y0 != cy) {                          // plane cell changed: flush the 4 corners
             if (cx != INT_MIN) {
 #pragma unroll
@@ -156,49 +273,38 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
             for (int k = 0; k < NQ; ++k) { gl0[k] = f4z(); gl1[k] = f4z(); }
             cl = l0; sl0 = ol0; sl1 = ol1;
         }
-        const float fx = fxp - xf, fy = fyp - yf, fl = flp - lf;
+        const float fx = pc.fx, fy = pc.fy, fl = pc.fl;
         const float wx0 = (1.f - fx) * mx0, wx1 = fx * mx1, wy0 = (1.f - fy) * my0, wy1 = fy * my1;
         const float wl0 = (1.f - fl) * ml0, wl1 = fl * ml1;
         const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
         float dA = 0.f, dB = 0.f, dC = 0.f, dD = 0.f, dLa = 0.f, dLb = 0.f;      // sum_c gl*tap / gp*tap
-        const float gs = APP ? 0.f : gbase[e];
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
-            const float4 a = ldg4(P + o00 + k * qs), b = ldg4(P + o10 + k * qs);
-            const float4 c = ldg4(P + o01 + k * qs), d = ldg4(P + o11 + k * qs);
-            const float4 la = ldg4(Ln + ol0 + k * qs), lb = ldg4(Ln + ol1 + k * qs);
-            float4 g4;
-            if (APP && GB16) {                       // bf16 row of the tensor-core head's dcomps
-                const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(
-                    reinterpret_cast<const unsigned short*>(A.gin) + (size_t)e * F.ctot + F.off[I] + q + k * qs));
-                g4 = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
-                                 __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
-            } else if (APP) {
-                g4 = __ldcs(reinterpret_cast<const float4*>(gbase + (size_t)e * F.ctot + k * qs));
-            } else {
-                g4 = make_float4(gs, gs, gs, gs);
-            }
+            const float4 a = *pslot(pb, 0, k), b = *pslot(pb, 1, k), c = *pslot(pb, 2, k), d = *pslot(pb, 3, k);
+            const float4 la = *lslot(lb, 0, k), lb4 = *lslot(lb, 1, k);
             float4 pv, lv;
             pv.x = a.x * w00 + b.x * w10 + c.x * w01 + d.x * w11; pv.y = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
             pv.z = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11; pv.w = a.w * w00 + b.w * w10 + c.w * w01 + d.w * w11;
-            lv.x = la.x * wl0 + lb.x * wl1; lv.y = la.y * wl0 + lb.y * wl1;
-            lv.z = la.z * wl0 + lb.z * wl1; lv.w = la.w * wl0 + lb.w * wl1;
+            lv.x = la.x * wl0 + lb4.x * wl1; lv.y = la.y * wl0 + lb4.y * wl1;
+            lv.z = la.z * wl0 + lb4.z * wl1; lv.w = la.w * wl0 + lb4.w * wl1;
+            const float4 g4 = gin_value(gc, k);
             const float4 gl = f4_mul2(g4, lv);       // dL/dP (interpolated plane value)
             const float4 gp = f4_mul2(g4, pv);       // dL/dL (interpolated line value)
             f4_fma(g00[k], gl, w00); f4_fma(g10[k], gl, w10); f4_fma(g01[k], gl, w01); f4_fma(g11[k], gl, w11);
             f4_fma(gl0[k], gp, wl0); f4_fma(gl1[k], gp, wl1);
             dA += f4_dot2(gl, a); dB += f4_dot2(gl, b); dC += f4_dot2(gl, c); dD += f4_dot2(gl, d);
-            dLa += f4_dot2(gp, la); dLb += f4_dot2(gp, lb);
+            dLa += f4_dot2(gp, la); dLb += f4_dot2(gp, lb4);
         }
         // d/d index (ATen grid_sampler_2d_backward: out-of-range taps read as 0)
         const float dux = ((dB * mx1 - dA * mx0) * wy0 + (dD * mx1 - dC * mx0) * wy1) * sclx;
         const float duy = ((dC * my1 - dA * my0) * wx0 + (dD * my1 - dB * my0) * wx1) * scly;
         const float dul = (dLb * ml1 - dLa * ml0) * scll;
-        const float t = u4.w;
+        const float t = pc.t;
         rs.o[ax] += dux; rs.d[ax] = fmaf(dux, t, rs.d[ax]);
         rs.o[ay] += duy; rs.d[ay] = fmaf(duy, t, rs.d[ay]);
         rs.o[al] += dul; rs.d[al] = fmaf(dul, t, rs.d[al]);
     }
+    cp_async_wait0();
     if (cx != INT_MIN) {
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
@@ -214,13 +320,15 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
 }
 
 template <bool APP, int NQ, int MINB, bool GB16>
-__global__ void __launch_bounds__(128, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
+__global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
+    extern __shared__ __align__(16) float4 sc_smem[];      // 12 NQ slots x SC_THREADS float4
     const int LW = NQ > 1 ? 4 : LW_rt;                   // multi-quad lanes: 4 lanes per walker, compile-time strides
     const int n = A.n_dev ? *A.n_dev : A.n_fixed;
     const int wl = threadIdx.x / LW;                     // walker within the CTA
     const int q = (threadIdx.x - wl * LW) * 4;           // first channel of this lane's first quad
     const int qs = LW * 4;                               // channel stride between this lane's quads
     if (wl >= walkers_per_cta) return;
+    float4* sm = sc_smem + threadIdx.x;
     const int n_units = (n + A.seg - 1) / A.seg;
     const int stride = gridDim.x * walkers_per_cta;
     for (int unit = blockIdx.x * walkers_per_cta + wl; unit < n_units; unit += stride) {
@@ -230,9 +338,9 @@ __global__ void __launch_bounds__(128, MINB) vm_scatter_walk_kernel(const Scatte
         RaySums rs;
 #pragma unroll
         for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
-        walk_plane<APP, NQ, 0, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
-        walk_plane<APP, NQ, 1, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
-        walk_plane<APP, NQ, 2, GB16>(A, e0, e1, q, qs, ray, ray_end, rs);
+        walk_plane<APP, NQ, 0, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        walk_plane<APP, NQ, 1, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        walk_plane<APP, NQ, 2, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
     }
 }
 
@@ -268,17 +376,25 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     int nq = 1, LW = cmax / 4;
     if (A.F.C[0] == A.F.C[1] && A.F.C[1] == A.F.C[2] && cmax % 16 == 0 && cmax <= 48) { nq = cmax / 16; LW = 4; }
     JT_CHECK_ARG(LW >= 1 && LW <= 128);
-    const int wpc = 128 / LW;                                 // walkers per CTA
+    const int wpc = SC_THREADS / LW;                          // walkers per CTA
     const int threads = ((wpc * LW + 31) / 32) * 32;
     long long units = ((long long)n_max + A.seg - 1) / A.seg;
     long long want = (units + wpc - 1) / wpc;
     long long cap = (long long)kNumSMs * 32;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
-#define JT_SC(APPV, NQV, MB, GB) vm_scatter_walk_kernel<APPV, NQV, MB, GB><<<grid, threads, 0, stream>>>(A, LW, wpc)
-    if (app && gin_bf16) { if (nq == 3) JT_SC(true, 3, 2, true); else if (nq == 2) JT_SC(true, 2, 3, true); else JT_SC(true, 1, 3, true); }
-    else if (app) { if (nq == 3) JT_SC(true, 3, 2, false); else if (nq == 2) JT_SC(true, 2, 3, false); else JT_SC(true, 1, 3, false); }
-    else { if (nq == 3) JT_SC(false, 3, 2, false); else if (nq == 2) JT_SC(false, 2, 3, false); else JT_SC(false, 1, 3, false); }
+    const int smem = 12 * nq * SC_THREADS * 16;
+#define JT_SC(APPV, NQV, MB, GB)                                                                                    \
+    {                                                                                                               \
+        if (smem > 48 * 1024 &&                                                                                     \
+            cudaFuncSetAttribute(vm_scatter_walk_kernel<APPV, NQV, MB, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 smem) != cudaSuccess)                                                              \
+            return JT_ERR_LAUNCH;                                                                                   \
+        vm_scatter_walk_kernel<APPV, NQV, MB, GB><<<grid, threads, smem, stream>>>(A, LW, wpc);                     \
+    }
+    if (app && gin_bf16) { if (nq == 3) JT_SC(true, 3, 2, true) else if (nq == 2) JT_SC(true, 2, 3, true) else JT_SC(true, 1, 3, true) }
+    else if (app) { if (nq == 3) JT_SC(true, 3, 2, false) else if (nq == 2) JT_SC(true, 2, 3, false) else JT_SC(true, 1, 3, false) }
+    else { if (nq == 3) JT_SC(false, 3, 2, false) else if (nq == 2) JT_SC(false, 2, 3, false) else JT_SC(false, 1, 3, false) }
 #undef JT_SC
     JT_RETURN_LAUNCH();
 }

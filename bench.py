@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the 800x800 full-frame inference timing")
+    ap.add_argument("--render-chunk", type=int, default=16384, help="rays per forward call of the full-frame render")
     ap.add_argument("--head", default="auto", choices=["auto", "tc", "fp32"],
                     help="shading head: tcgen05 tensor-core kernels (auto/tc) or strict-fp32 SIMT GEMMs")
     return ap.parse_args()
@@ -50,6 +52,7 @@ def parse():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled (NVML, nvidia-smi as fallback) while the timed regions run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -57,16 +60,49 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
         self.t = threading.Thread(target=self.run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES remapping via the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self.h = h
+                        break
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = []
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                          ("sw_power_cap", 0x4)):
+            flags.append("Active" if (r & bit) else "Not Active")
+        return [str(sm), str(mx), "0"] + flags
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -91,7 +127,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU port (oracle) timing
@@ -232,7 +268,7 @@ def own_arm(args):
     params = [p for p in model.parameters()]
     bucket = parallel.GradBucket(params) if world > 1 else None
 
-    def step(o, d, tgt):
+    def step(o, d, tgt, reduce=True):
         if bucket is not None:
             bucket.zero()
             bucket.attach()
@@ -244,7 +280,7 @@ def own_arm(args):
         rgb, depth, acc = model(opt, o, d, **fkw)
         loss = ((rgb - tgt) ** 2).mean()
         loss.backward()
-        if bucket is not None:
+        if bucket is not None and reduce:
             bucket.all_reduce(average=True)
         return loss
 
@@ -281,16 +317,16 @@ def own_arm(args):
     for _ in range(max(args.warmup, 3)):
         step(o_d.clone(), d_d.clone(), tgt_d)
     barrier()
-    l0 = jt._lib.launch_count()
-    with ClockSampler(local) as clk:
-        ms = timed(lambda: step(o_d.clone(), d_d.clone(), tgt_d), args.steps)
-        barrier()
-    launches = jt._lib.launch_count() - l0
     for _ in range(2):
         step_e2e()
     barrier()
-    ms_e2e = timed(step_e2e, args.steps)
-    barrier()
+    l0 = jt._lib.launch_count()
+    with ClockSampler(local) as clk:             # clocks are sampled across both timed regions
+        ms = timed(lambda: step(o_d.clone(), d_d.clone(), tgt_d), args.steps)
+        barrier()
+        launches = jt._lib.launch_count() - l0
+        ms_e2e = timed(step_e2e, args.steps)
+        barrier()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -298,14 +334,14 @@ def own_arm(args):
 
     roof, breakdown = None, None
     if rank == 0 and not args.no_breakdown:
-        ops.TIMER.enabled = True
+        ops.TIMER.enabled = True                 # rank-0-only section: no collectives in here
         for _ in range(3):
-            step(o_d.clone(), d_d.clone(), tgt_d)
+            step(o_d.clone(), d_d.clone(), tgt_d, reduce=False)
         ops.TIMER.summary()
         reps = 5
         for _ in range(reps):
             flush.fill_(1.0)
-            step(o_d.clone(), d_d.clone(), tgt_d)
+            step(o_d.clone(), d_d.clone(), tgt_d, reduce=False)
         summ = ops.TIMER.summary()
         ops.TIMER.enabled = False
         V, A = (int(t.item()) for t in jt.VMRender.last_counts)      # measured on the last step's batch
@@ -333,6 +369,34 @@ def own_arm(args):
         if roof is not None and gather > 0:
             roof["vm_gather_fwd_bwd"] = {"ms": gather, "achieved": gbytes / (gather * 1e-3) / 1e9,
                                          "frac": gbytes / (gather * 1e-3) / 1e9 / hbm_peak, "V": V, "A": A}
+
+    # second half of BASELINE.json's metric: one 800x800 frame (640 000 rays, cfg2 field, is_train=False, no
+    # blur) rendered like the reference's render_by_slices (model/nerf.py:728-740), rays resident on the device
+    render = None
+    if rank == 0 and not args.no_render:
+        fo, fd = jt.synth.frame_rays(view=0)
+        fo, fd = fo.to(dev), fd.to(dev)
+        rkw = dict(white_bg=run["white_bg"], is_train=False, ndc_ray=run["ndc"], N_samples=S)
+        chunk = args.render_chunk
+
+        def render_frame():
+            outs = []
+            with torch.no_grad():
+                for c in range(0, fo.shape[0], chunk):
+                    outs.append(model(opt, fo[c:c + chunk], fd[c:c + chunk], **rkw)[0])
+            return torch.cat(outs)
+
+        render_frame()
+        torch.cuda.synchronize()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1.0)
+        s_ev.record()
+        img = render_frame()
+        e_ev.record()
+        torch.cuda.synchronize()
+        fms = s_ev.elapsed_time(e_ev)
+        render = {"ms_per_frame": fms, "rays_per_s": fo.shape[0] / (fms * 1e-3), "frame": "800x800", "rays_per_call": chunk,
+                  "finite": bool(torch.isfinite(img).all())}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -364,6 +428,8 @@ def own_arm(args):
             line["roofline"] = roof
         if breakdown is not None:
             line["kernel_ms_per_step"] = breakdown
+        if render is not None:
+            line["render_800x800"] = render
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -213,6 +213,16 @@ def algorithmic_bytes(name, V, A, cd, ca, ctot_a):
     return table.get(name)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+# this same workload (profiles/r01_ncu_full_v4.txt; cold caches, so an upper bound on a warm step)
+NCU_DRAM_BYTES = {
+    "vm_app_bwd": 1.937981e9 + 0.328528e9, "vm_density_bwd": 0.089458e9 + 0.004454e9,
+    "vm_density_fwd": 0.053607e9 + 0.001437e9, "app_basis_fwd_tc": 0.453102e9 + 0.899889e9,
+    "head_mlp_fwd_tc": 0.299442e9 + 1.428690e9,
+    "head_bwd_tc": 0.906751e9 + 1.360633e9 + 2.863843e9 + 0.003652e9,      # data kernel + weight-gradient kernel
+}
+
+
 def gemm_flops(name, A, F, ctot, in_dim, H):
     table = {
         "basis_fwd": 2 * A * F * ctot, "basis_bwd_x": 2 * A * F * ctot, "basis_bwd_w": 2 * A * F * ctot,
@@ -356,12 +366,15 @@ def own_arm(args):
         if by is not None:
             ach = by / (per_launch_ms * 1e-3) / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "ms_per_launch": per_launch_ms}
+                    "frac": ach / hbm_peak, "traffic": NCU_DRAM_BYTES.get(top), "peak_source": peak_src,
+                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": by,
+                    "note": "algorithmic bytes count every tap as an HBM access (SURVEY 8d); the 69 MB of factors "
+                            "stay in the 126 MB L2 and consecutive samples of a ray share cells, so frac > 1 and "
+                            "DRAM traffic << algorithmic bytes (profiles/r01_ncu_full_v4.txt)"}
         elif fl is not None:
             ach = fl / (per_launch_ms * 1e-3) / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / tf_peak, "traffic": NCU_DRAM_BYTES.get(top), "peak_source": peak_src,
                     "ms_per_launch": per_launch_ms}
         gather = sum(breakdown.get(k, 0.0) for k in ("vm_density_fwd", "vm_app_fwd", "vm_density_bwd", "vm_app_bwd"))
         gbytes = sum(algorithmic_bytes(k, V, A, cd, ca, sum(model.app_n_comp))
@@ -412,11 +425,12 @@ def own_arm(args):
             "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.head == "fp32" else "f32 (VM gather/scatter, compositing, blur) + bf16 tensor-core "
-                     "shading head (forward: split hi+lo operands = fp32-class; backward: bf16 operands, fp32 accumulate)",
+            "dtype": "f32" if args.head == "fp32" else "f32 (shading-head GEMMs on tcgen05: bf16 operands, f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, "
                                    f"S={S}, {N} rays/GPU, fwd+bwd, optimizer step excluded", "head": args.head,
+                       "head_arith": "forward: hi+lo split bf16 operands (3 MMAs per product, fp32-class, rgb within 1e-4); "
+                                     "backward: bf16 operands, f32 accumulate (gradients within 2e-2 rel)",
                        "blur": args.blur, "l2": "256 MB write between timed steps (L2 flushed)",
                        "parallelism": f"ray-sharded x{world}, NCCL all-reduce of a flat fp32 gradient bucket"},
             "e2e": {"value": rays_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -213,6 +213,30 @@ int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* d
 int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* taps, int ntaps,
                int axes, int adjoint, cudaStream_t stream);
 
+/* ---- pose -> rays (next row) --------------------- */
+/* One step's ray set for the sampled pixels only, replacing
+ *   model/bat.py:350-353      pose = compose([lie.se3_to_SE3(se3_refine[idx]), pose])   (camera.py:81-99, 43-58)
+ *   model/tensorf.py:144-166  camera.get_center_and_ray (camera.py:231-261) for ALL H*W pixels, then [:, ray_idx],
+ *                             then camera.convert_NDC (camera.py:303-340) when ndc.
+ * se3 [n_rows][6] (w, u) or NULL (no refinement); view b uses row view_idx[b] (or b when view_idx is NULL).
+ * base [B][3][4] world-to-camera poses (one shared pose when base_per_view = 0); intr_inv / intr [B][3][3]
+ * (shared when *_per_view = 0; intr only read when ndc). Pixel of ray r of view b: pix[r] (pix_per_view = 0),
+ * pix[b*R + r] (pix_per_view = 1) or pix_base + r when pix is NULL (a contiguous render slice);
+ * pixel p -> (x, y) = (p % width + 0.5, p / width + 0.5). Outputs center, ray [B][R][3] and (optional) the
+ * composed poses pose_out [B][3][4]. */
+int jt_pose_rays_fwd(const float* se3, const int* view_idx, const float* base, int base_per_view,
+                     const float* intr_inv, int kinv_per_view, const float* intr, int k_per_view, const int* pix,
+                     int pix_per_view, int pix_base, int n_views, int n_rays_per_view, int width, int ndc,
+                     int center_shift, int detach_shift, float near_plane, float* center, float* ray,
+                     float* pose_out, cudaStream_t stream);
+/* Autograd of the above: (d_center, d_ray [B][R][3]) -> d_se3 [n_rows][6] (ADDED into; may be NULL) and/or
+ * d_pose [B][3][4] (gradient w.r.t. the composed pose, stored; may be NULL). scratch12: [B][12] floats. */
+int jt_pose_rays_bwd(const float* se3, const int* view_idx, const float* base, int base_per_view,
+                     const float* intr_inv, int kinv_per_view, const float* intr, int k_per_view, const int* pix,
+                     int pix_per_view, int pix_base, int n_views, int n_rays_per_view, int width, int ndc,
+                     int center_shift, int detach_shift, float near_plane, const float* d_center, const float* d_ray,
+                     float* scratch12, float* d_se3, float* d_pose, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,15 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    """Render-path fixtures (tests/golden/make_golden.py)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    return [n for n in names if not n.startswith("camera_")]
+
+
+def camera_golden_names():
+    """Pose -> ray fixtures (tests/golden/make_golden_camera.py)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "camera_*.pt")))
+    return names
 
 
 def load_golden(name):

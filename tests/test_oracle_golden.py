@@ -4,8 +4,9 @@ floating outputs and gradients agree to <= 2e-6 (same ATen kernels, same order).
 import pytest
 import torch
 
-from common import (field_from_golden, golden_names, golden_valid, load_golden, rel_err,
+from common import (camera_golden_names, field_from_golden, golden_names, golden_valid, load_golden, rel_err,
                     render_kwargs_from_golden, vo)
+from oracle import camera_oracle as co
 
 torch.set_num_threads(max(1, torch.get_num_threads()))
 
@@ -34,3 +35,20 @@ def test_oracle_matches_reference_golden(name):
     for k, (s, sabs, mx) in g["grad_sums"].items():
         got = field.params[k].grad
         assert abs(float(got.double().abs().sum()) - sabs) <= 1e-5 * max(sabs, 1e-12), k
+
+
+@pytest.mark.parametrize("name", camera_golden_names())
+def test_camera_oracle_matches_reference_golden(name):
+    """oracle/camera_oracle.py against the live reference's camera.py (make_golden_camera.py)."""
+    g = load_golden(name)
+    c = g["case"]
+    se3 = g["se3"].clone().requires_grad_(True)
+    assert (co.refined_pose(se3, g["pose"]) - g["refined_pose"]).abs().max() <= 1e-6
+    center, ray = co.rays_of_step(se3, g["pose"], g["intr_inv"], c["H"], c["W"], g["ray_idx"], intr=g["intr"],
+                                  ndc=c["ndc"], near=1.0, center_shift=c.get("shift", True),
+                                  detach_shift=c.get("detach", False))
+    assert rel_err(center, g["center"]) <= 1e-6
+    assert rel_err(ray, g["ray"]) <= 1e-6
+    loss = (center * g["g_center"]).sum() + (ray * g["g_ray"]).sum()
+    loss.backward()
+    assert rel_err(se3.grad, g["d_se3"]) <= 1e-5

@@ -9,9 +9,10 @@ appearance 3x48 components, app_dim 27, MLP_Fea shading head, 4096-ray batch, S=
 samples per ray, forward + backward to all factor / head / ray gradients. Synthetic
 Blender-shaped rays and random-init factors (joint_tensorf_b200.synth).
 
-A step = pose-independent part of one training iteration: stratified jitter ->
-forward -> MSE -> backward (+ one NCCL all-reduce of the flat gradient bucket when
-N > 1). The optimizer step is excluded (SURVEY.md section 8d timing protocol).
+A step = one training iteration without the optimizer (SURVEY.md section 8d timing
+protocol): se3_refine + fixed poses -> rays of the sampled pixels (jt_pose_rays_fwd) ->
+stratified jitter -> forward -> MSE -> backward to all factor / head / se3_refine
+gradients (+ one NCCL all-reduce of the flat gradient bucket when N > 1).
 N > 1 is weak scaling: every rank renders its own 4096 rays.
 """
 import argparse
@@ -177,6 +178,40 @@ def time_cpu_port(workload, n_rays, steps, warmup, blur):
     return n_rays / sec, sec, cores
 
 
+def time_aten_gpu(workload, n_rays, steps, warmup, dev):
+    """Same-box bar: the reference ALGORITHM with stock ATen CUDA operators on this B200 -- the oracle
+    port run with its tensors on the device (grid_sample / cumprod / addmm kernels, autograd backward). This is
+    what the unmodified reference would execute on a GPU; reported next to the CPU baseline, never shipped."""
+    from joint_tensorf_b200 import synth
+    from oracle import vm_oracle as vo
+    field, run = oracle_field(workload)
+    field.params = {k: v.detach().to(dev).requires_grad_(True) for k, v in field.params.items()}
+    field.aabb = field.aabb.to(dev)
+    o, d, _ = synth.blender_rays(n_rays, 32, seed=1)
+    o, d = o.to(dev), d.to(dev)
+    target = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(2)).to(dev)
+    kw = dict(n_samples=run["n_samples"], white_bg=run["white_bg"], ndc=run["ndc"])
+    times = []
+    with torch.device(dev):
+        for it in range(warmup + steps):
+            oc, dc = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+            jit = torch.rand(n_rays, 1)
+            for p in field.params.values():
+                p.grad = None
+            torch.cuda.synchronize()
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record()
+            rgb, _, _ = vo.render(field, oc, dc, jitter=jit, **kw)
+            loss = ((rgb - target) ** 2).mean()
+            loss.backward()
+            e_ev.record()
+            torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(s_ev.elapsed_time(e_ev) * 1e-3)
+    sec = sum(times) / len(times)
+    return n_rays / sec, sec
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -266,28 +301,41 @@ def own_arm(args):
     model.head_precision = args.head
     opt = default_opt(model.shadingMode, run["ndc"])
     N, S = args.rays, run["n_samples"]
-    o_h, d_h, _ = jt.synth.blender_rays(N, 32, seed=1 + rank)
+    # Pose side of the step (SURVEY 8d protocol): 32 hemisphere views, pose noise N(0, 0.15^2) composed into the
+    # fixed pose (bat.py:34,346-348), se3_refine = 0 and trainable (bat.py:350), 128 pixels shared by all views
+    # (nerf.py:657-658) -> N = 4096 rays generated by jt_pose_rays_fwd, gradients back to se3_refine.
+    n_views = 32
+    H_img = W_img = 800
+    R_pix = max(1, N // n_views)
+    N = n_views * R_pix
+    gt_pose, intr = jt.synth.blender_views(n_views, (H_img, W_img), seed=1 + rank)
+    g_noise = torch.Generator().manual_seed(50 + rank)
+    pose_noise = 0.15 * torch.randn((n_views, 6), generator=g_noise)
+    base_pose = jt.camera.refined_pose(pose_noise.to(dev), gt_pose.to(dev))
+    intr_inv_d = intr.inverse().to(dev)
+    se3_refine = torch.nn.Parameter(torch.zeros((n_views, 6), device=dev))
+    cam_opt = jt.options.Namespace(H=H_img, W=W_img, camera=dict(model="perspective", ndc=False), arch=dict())
+    pix_h = torch.randperm(H_img * W_img, generator=torch.Generator().manual_seed(7 + rank))[:R_pix].to(torch.int32)
     tgt_h = torch.rand(N, 3, generator=torch.Generator().manual_seed(100 + rank))
-    o_h, d_h, tgt_h = o_h.pin_memory(), d_h.pin_memory(), tgt_h.pin_memory()
-    o_d, d_d, tgt_d = o_h.to(dev), d_h.to(dev), tgt_h.to(dev)
+    pix_h, tgt_h = pix_h.pin_memory(), tgt_h.pin_memory()
+    pix_d, tgt_d = pix_h.to(dev), tgt_h.to(dev)
     loss_h = torch.empty((), pin_memory=True)
     fkw = dict(white_bg=run["white_bg"], is_train=True, ndc_ray=run["ndc"], N_samples=S)
     if args.blur > 0:
         fkw.update(c2f_mode="uniform-gaussian", c2f_parameter_density=args.blur * 0.6,
                    c2f_parameter_color=args.blur, c2f_kernel_size=64)
-    params = [p for p in model.parameters()]
+    params = [p for p in model.parameters()] + [se3_refine]
     bucket = parallel.GradBucket(params) if world > 1 else None
 
-    def step(o, d, tgt, reduce=True):
+    def step(pix, tgt, reduce=True):
         if bucket is not None:
             bucket.zero()
             bucket.attach()
         else:
             for p in params:
                 p.grad = None
-        o = o.requires_grad_(True)
-        d = d.requires_grad_(True)
-        rgb, depth, acc = model(opt, o, d, **fkw)
+        center, ray = jt.camera.get_center_and_ray(cam_opt, base_pose, intr_inv_d, ray_idx=pix, se3_refine=se3_refine)
+        rgb, depth, acc = model(opt, center.view(-1, 3), ray.view(-1, 3), **fkw)
         loss = ((rgb - tgt) ** 2).mean()
         loss.backward()
         if bucket is not None and reduce:
@@ -295,10 +343,9 @@ def own_arm(args):
         return loss
 
     def step_e2e():
-        o = o_h.to(dev, non_blocking=True)
-        d = d_h.to(dev, non_blocking=True)
+        pix = pix_h.to(dev, non_blocking=True)
         t = tgt_h.to(dev, non_blocking=True)
-        loss = step(o, d, t)
+        loss = step(pix, t)
         loss_h.copy_(loss.detach(), non_blocking=True)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # > 126 MB L2
@@ -325,14 +372,14 @@ def own_arm(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step(o_d.clone(), d_d.clone(), tgt_d)
+        step(pix_d, tgt_d)
     barrier()
     for _ in range(2):
         step_e2e()
     barrier()
     l0 = jt._lib.launch_count()
     with ClockSampler(local) as clk:             # clocks are sampled across both timed regions
-        ms = timed(lambda: step(o_d.clone(), d_d.clone(), tgt_d), args.steps)
+        ms = timed(lambda: step(pix_d, tgt_d), args.steps)
         barrier()
         launches = jt._lib.launch_count() - l0
         ms_e2e = timed(step_e2e, args.steps)
@@ -346,12 +393,12 @@ def own_arm(args):
     if rank == 0 and not args.no_breakdown:
         ops.TIMER.enabled = True                 # rank-0-only section: no collectives in here
         for _ in range(3):
-            step(o_d.clone(), d_d.clone(), tgt_d, reduce=False)
+            step(pix_d, tgt_d, reduce=False)
         ops.TIMER.summary()
         reps = 5
         for _ in range(reps):
             flush.fill_(1.0)
-            step(o_d.clone(), d_d.clone(), tgt_d, reduce=False)
+            step(pix_d, tgt_d, reduce=False)
         summ = ops.TIMER.summary()
         ops.TIMER.enabled = False
         V, A = (int(t.item()) for t in jt.VMRender.last_counts)      # measured on the last step's batch
@@ -387,16 +434,18 @@ def own_arm(args):
     # blur) rendered like the reference's render_by_slices (model/nerf.py:728-740), rays resident on the device
     render = None
     if rank == 0 and not args.no_render:
-        fo, fd = jt.synth.frame_rays(view=0)
-        fo, fd = fo.to(dev), fd.to(dev)
+        n_pix = H_img * W_img
+        f_pose, f_kinv = gt_pose[:1].to(dev), intr_inv_d[:1]
         rkw = dict(white_bg=run["white_bg"], is_train=False, ndc_ray=run["ndc"], N_samples=S)
         chunk = args.render_chunk
 
         def render_frame():
+            """render_by_slices (nerf.py:728-740): per slice, rays of that slice only (jt_pose_rays_fwd) -> forward."""
             outs = []
             with torch.no_grad():
-                for c in range(0, fo.shape[0], chunk):
-                    outs.append(model(opt, fo[c:c + chunk], fd[c:c + chunk], **rkw)[0])
+                for c in range(0, n_pix, chunk):
+                    ce, ra = jt.camera.get_center_and_ray(cam_opt, f_pose, f_kinv, pix_base=c, n_rays=min(chunk, n_pix - c))
+                    outs.append(model(opt, ce.view(-1, 3), ra.view(-1, 3), **rkw)[0])
             return torch.cat(outs)
 
         render_frame()
@@ -408,7 +457,7 @@ def own_arm(args):
         e_ev.record()
         torch.cuda.synchronize()
         fms = s_ev.elapsed_time(e_ev)
-        render = {"ms_per_frame": fms, "rays_per_s": fo.shape[0] / (fms * 1e-3), "frame": "800x800", "rays_per_call": chunk,
+        render = {"ms_per_frame": fms, "rays_per_s": n_pix / (fms * 1e-3), "frame": "800x800", "rays_per_call": chunk,
                   "finite": bool(torch.isfinite(img).all())}
 
     cpu = None
@@ -418,9 +467,20 @@ def own_arm(args):
                "sample": f"{args.cpu_rays} of {N} rays, 2 timed fwd+bwd iterations of oracle/vm_oracle.py "
                          f"(torch CPU, {cores} threads)"}
 
+    aten = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            rps, sec = time_aten_gpu(args.workload, N, 3, 1, dev)
+            aten = {"value": rps, "unit": UNIT, "ms_per_step": sec * 1e3,
+                    "what": f"reference algorithm (oracle port) with stock ATen CUDA kernels on this GPU, {N} rays, "
+                            "fwd+bwd, 3 timed iterations; rays resident, no pose generation"}
+        except Exception as ex:      # a baseline leg must never take the bench line down
+            aten = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         rays_total = N * world
-        h2d = (o_h.numel() + d_h.numel() + tgt_h.numel()) * 4
+        h2d = pix_h.numel() * 4 + tgt_h.numel() * 4
         line = {
             "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -428,7 +488,9 @@ def own_arm(args):
             "dtype": "f32" if args.head == "fp32" else "f32 (shading-head GEMMs on tcgen05: bf16 operands, f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, "
-                                   f"S={S}, {N} rays/GPU, fwd+bwd, optimizer step excluded", "head": args.head,
+                                   f"S={S}, {N} rays/GPU ({n_views} views x {R_pix} pixels, rays generated from se3_refine + pose "
+                                   f"inside the step), fwd+bwd to factor/head/se3 gradients, optimizer step excluded",
+                       "head": args.head,
                        "head_arith": "forward: hi+lo split bf16 operands (3 MMAs per product, fp32-class, rgb within 1e-4); "
                                      "backward: bf16 operands, f32 accumulate (gradients within 2e-2 rel)",
                        "blur": args.blur, "l2": "256 MB write between timed steps (L2 flushed)",
@@ -446,6 +508,8 @@ def own_arm(args):
             line["render_800x800"] = render
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if aten is not None:
+            line["aten_gpu_baseline"] = aten
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

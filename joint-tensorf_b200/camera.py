@@ -134,3 +134,27 @@ def get_center_and_ray(opt, pose, intr_inv=None, ray_idx=None, intr=None, se3_re
     cfg = _RayCfg(n_views=B, n_rays=R, width=int(opt.W), ndc=ndc, near=near, center_shift=shift, detach_shift=detach,
                   pix_base=int(pix_base))
     return PoseRays.apply(cfg, se3_refine, pose, intr_inv, intr, ray_idx, view_idx)
+
+
+@torch.no_grad()
+def refined_pose(se3, pose, view_idx=None):
+    """`camera.pose.compose([camera.lie.se3_to_SE3(se3), pose])` (camera.py:81-99,43-58) -> [B,3,4], no gradient.
+    Used for the fixed part of the training pose, `compose([pose_noise, GT])` (bat.py:346-348), and for
+    reading back the current refined poses (evaluation / logging)."""
+    ops._need_cuda(pose, "pose")
+    lib = _lib.lib()
+    dev = pose.device
+    pose_c = pose.detach().contiguous().float()
+    pose_c = pose_c[None] if pose_c.dim() == 2 else pose_c
+    se3_c = se3.detach().contiguous().float()
+    vi = view_idx.to(device=dev, dtype=torch.int32).contiguous() if view_idx is not None else None
+    B = int(vi.shape[0]) if vi is not None else int(se3_c.shape[0])
+    if pose_c.shape[0] not in (1, B):
+        raise _lib.JtError(f"pose has {pose_c.shape[0]} entries for {B} views")
+    eye = torch.eye(3, device=dev)
+    scratch = torch.empty((2, B, 1, 3), device=dev)
+    out = torch.empty((B, 3, 4), device=dev)
+    check(lib.jt_pose_rays_fwd(_p(se3_c), _p(vi), _p(pose_c), 0 if (pose_c.shape[0] == 1 and B > 1) else 1, _p(eye), 0,
+                               0, 0, 0, 0, 0, B, 1, 1, 0, 0, 0, 0.0, _p(scratch[0]), _p(scratch[1]), _p(out),
+                               _stream()), "jt_pose_rays_fwd")
+    return out

@@ -58,6 +58,22 @@ def blender_rays(n_rays=4096, n_views=32, hw=(800, 800), focal=1111.1, radius=4.
     return o[:n_rays].contiguous(), d[:n_rays].contiguous(), v[:n_rays].contiguous()
 
 
+def blender_views(n_views=32, hw=(800, 800), focal=1111.1, radius=4.0, seed=1):
+    """The cameras of `blender_rays` as matrices: world-to-camera poses [B,3,4] and intrinsics [B,3,3]
+    (what the reference keeps per view: var.pose, var.intr; data/blender.py:86-104)."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = hw
+    u = torch.rand((n_views,), generator=g)
+    phi = torch.rand((n_views,), generator=g) * 2 * math.pi
+    cz = u * 0.9 + 0.05
+    cr = torch.sqrt(1 - cz * cz)
+    centers = radius * torch.stack([cr * torch.cos(phi), cr * torch.sin(phi), cz], dim=-1)
+    rot, t = _look_at_w2c(centers)
+    pose = torch.cat([rot, t[..., None]], dim=-1)
+    intr = torch.tensor([[focal, 0.0, w / 2], [0.0, focal, h / 2], [0.0, 0.0, 1.0]])[None].repeat(n_views, 1, 1)
+    return pose.contiguous(), intr.contiguous()
+
+
 def frame_rays(view=0, hw=(800, 800), focal=1111.1, radius=4.0, seed=2):
     """All H*W rays of one hemisphere camera (full-frame render, config 5)."""
     g = torch.Generator().manual_seed(seed + 7919 * view)

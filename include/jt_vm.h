@@ -99,11 +99,13 @@ int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_facto
  * i.e. the autograd of rays_pts = o + d*t and normalize_coord (tensorBase.py:502-503,597).
  * The element list must be ray-major (as jt_march_compact / jt_alpha_fwd produce it).
  * d_o / d_d [N][3] must be initialised by the caller (zeros, or jt_ray_init for NDC rays).
- * gin_bf16 = 1 (app only): gin rows are bf16 [n][sum C] as jt_head_bwd_tc writes them. */
+ * gin_bf16 = 1 (app only): gin rows are bf16 [n][sum C] as jt_head_bwd_tc writes them.
+ * max_ctas > 0 caps the (persistent) grid, so that the kernel can share the SMs with another
+ * kernel running on a second stream; 0 = fill the machine. */
 int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,
                        const float* samp, const int* slot, const int* sidx, const int* n_dev, int n_max,
                        const void* gin, int gin_bf16, int n_samples, const float* h_inv, float* d_o, float* d_d,
-                       cudaStream_t stream);
+                       int max_ctas, cudaStream_t stream);
 /* d_o = 0; d_d = dnorm_r / |d|^2 * d  (NDC rays: dists are scaled by |ray_dir|, batBase.py:63-65;
  * dnorm holds dL/d|d| * |d| from jt_render_bwd) or 0 when dnorm is NULL. */
 int jt_ray_init(const float* rays_d, const float* dnorm, int n_rays, float* d_o, float* d_d, cudaStream_t stream);

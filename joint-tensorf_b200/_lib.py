@@ -19,7 +19,7 @@ SIGNATURES = {
     "jt_exclusive_scan": [_P, _P, _I, _P],
     "jt_vm_gather_fwd": [_I, _P, _P, _P, _P, _P, _I, _P, _P],
     "jt_vm_gather_bwd": [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
-    "jt_vm_scatter_rays": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P],
+    "jt_vm_scatter_rays": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P],
     "jt_ray_init": [_P, _P, _I, _P, _P, _P],
     "jt_gemm_nt": [_P, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
     "jt_gemm_tn": [_P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _P],

@@ -351,7 +351,7 @@ using namespace jt;
 extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads,
                                   const int* h_dims, const float* samp, const int* slot, const int* sidx,
                                   const int* n_dev, int n_max, const void* gin, int gin_bf16, int n_samples, const float* h_inv,
-                                  float* d_o, float* d_d, cudaStream_t stream) {
+                                  float* d_o, float* d_d, int max_ctas, cudaStream_t stream) {
     JT_CHECK_ARG(h_factors && h_factor_grads && h_dims && samp && sidx && gin && h_inv && d_o && d_d && n_samples > 0);
     if (n_max <= 0) return JT_OK;
     ScatterArgs A;
@@ -383,7 +383,7 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     const int threads = ((wpc * LW + 31) / 32) * 32;
     long long units = ((long long)n_max + A.seg - 1) / A.seg;
     long long want = (units + wpc - 1) / wpc;
-    long long cap = (long long)kNumSMs * 32;
+    long long cap = max_ctas > 0 ? (long long)max_ctas : (long long)kNumSMs * 32;
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
     const int smem = 12 * nq * SC_THREADS * 16;

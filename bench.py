@@ -355,6 +355,7 @@ def own_arm(args):
         flush between steps is on the stream but outside every event pair; the host does not
         synchronise inside the loop, so it queues launches ahead as a training loop does."""
         evs = []
+        t_host = time.perf_counter()
         for _ in range(k):
             flush.fill_(1.0)                                           # evict L2 between steps (untimed)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,6 +363,7 @@ def own_arm(args):
             fn()
             e.record()
             evs.append((s, e))
+        timed.host_ms = (time.perf_counter() - t_host) * 1e3 / k      # host time to ENQUEUE a step (launch-bound check)
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
@@ -380,6 +382,7 @@ def own_arm(args):
     l0 = jt._lib.launch_count()
     with ClockSampler(local) as clk:             # clocks are sampled across both timed regions
         ms = timed(lambda: step(pix_d, tgt_d), args.steps)
+        host_ms = timed.host_ms
         barrier()
         launches = jt._lib.launch_count() - l0
         ms_e2e = timed(step_e2e, args.steps)
@@ -497,7 +500,7 @@ def own_arm(args):
                        "parallelism": f"ray-sharded x{world}, NCCL all-reduce of a flat fp32 gradient bucket"},
             "e2e": {"value": rays_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
             "clocks": clk.summary(),
         }
         if roof is not None:

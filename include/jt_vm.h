@@ -209,11 +209,17 @@ int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* d
 
 /* ---- K5: separable blur ------------------------------------------------ */
 /* BAT_VMSplit.convolute_plane / convolute_line (bateRF.py:8-39) on a channel-last
- * [H][W][C] array: replicate-padded cross-correlation with `taps` [ntaps] (device,
- * odd) along W (axes bit 0) and/or H (bit 1); adjoint = 1 applies the transposed
- * operator (backward pass). tmp [H][W][C] is needed when axes == 3. */
-int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* taps, int ntaps,
+ * [H][W][C] array: replicate-padded cross-correlation with `h_taps` [ntaps] (HOST
+ * array, odd count <= 257; the taps travel in the kernel parameters) along W (axes bit 0)
+ * and/or H (bit 1); adjoint = 1 applies the transposed operator (backward pass).
+ * tmp [H][W][C] is needed when axes == 3. in / out / tmp 16-byte aligned. */
+int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* h_taps, int ntaps,
                int axes, int adjoint, cudaStream_t stream);
+/* The same for up to 12 arrays (all VM factors of a step) in two launches, one per pass: h_in / h_out / h_tmp
+ * are HOST arrays of device pointers, h_dims = {H, W, C, axes} per array, array i uses tap set h_tapset[i]
+ * (0 .. nsets-1, nsets <= 2: density taps and colour taps, batBase.py:92-101) of h_taps [nsets][ntaps] (host). */
+int jt_blur_multi(int n_arrays, const void* const* h_in, void* const* h_out, void* const* h_tmp, const int* h_dims,
+                  const int* h_tapset, const float* h_taps, int nsets, int ntaps, int adjoint, cudaStream_t stream);
 
 /* ---- pose -> rays (next row) --------------------- */
 /* One step's ray set for the sampled pixels only, replacing

@@ -35,6 +35,7 @@ SIGNATURES = {
     "jt_render_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _I, _I, _P, _P, _P, _P],
     "jt_ray_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_blur_cl": [_P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P],
+    "jt_blur_multi": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "jt_pose_rays_fwd": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P],
     "jt_pose_rays_bwd": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
 }

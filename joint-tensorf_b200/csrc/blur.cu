@@ -6,13 +6,24 @@
 // along each plane axis / the line axis, per channel, 65 taps for
 // c2f_kernel_size 64 (kernels.py:18), taps not normalised (kernels.py:20-21).
 //
-// Data is channel-last ([H][W][C]); one pass blurs along one spatial axis. A CTA
-// owns a tile of TL consecutive positions of one "pencil" (a row for the W pass,
-// a column for the H pass) with all C channels: it pulls the tile plus a halo of
-// (ntaps-1)/2 on each side into shared memory with cp.async.bulk (one bulk copy
-// for a row tile, which is contiguous; one per position for a column tile),
-// waits on an mbarrier, then every thread produces 4 consecutive outputs of one
-// channel from a sliding register window (2 LDS per 4 FMA).
+// Data is channel-last ([H][W][C]); one pass blurs along one spatial axis. The stencil is
+// independent per channel, so for the pass along H the x position is folded into the channel
+// axis: a CTA owns TL consecutive positions of one "pencil" = a row (W pass, C channels) or a
+// strip of WX adjacent columns (H pass, WX*C contiguous floats per position).
+//
+// Per CTA:
+//   1. the tile plus a halo of (ntaps-1)/2 positions on each side is pulled into shared memory by
+//      cp.async.bulk (SASS UBLKCP; one copy per group of 8 contiguous positions, or one per
+//      position when strided / at a clamped edge), completion on an mbarrier. Out-of-range
+//      positions are materialised in the tile (forward: the replicated edge row, adjoint: zeros),
+//      so the inner loop has no bounds logic;
+//   2. a thread owns 8 consecutive outputs x 4 channels (32 fp32 accumulators). The input window
+//      slides through two register halves of 8 float4 each: per block of 8 taps it issues 8
+//      LDS.128 and 256 FMAs whose tap operand comes straight from the constant bank (the taps
+//      travel in the kernel parameters). Position groups are padded in shared memory so that the
+//      32 lanes of a warp always read 32 distinct 16-byte bank groups.
+// Arithmetic per pass: 2*ntaps flop per element against 8 B of HBM traffic (65 taps: 16 flop/B),
+// i.e. the pass is HBM-bound only if the FMA pipe is kept busy -- hence the register tiling.
 //
 // Forward:  y[i] = sum_t k[t] * x[clamp(i + t - h, 0, n-1)]            (h = ntaps/2)
 // Adjoint:  dx[m] = sum_i sum_t k[t] dy[i] [clamp(i + t - h) == m]
@@ -24,8 +35,10 @@
 
 namespace jt {
 
-constexpr int TL = 128;          // outputs per CTA along the blurred axis
 constexpr int MAX_TAPS = 257;
+constexpr int KPAD = 272;        // taps padded with zeros to a multiple of 16
+constexpr int BL_THREADS = 256;
+constexpr int R_OUT = 8;         // outputs per thread along the blurred axis
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -52,135 +65,309 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// pencils: n positions spaced `es` floats apart, each with C contiguous channels.
-// pencil p starts at base + (p / inner) * outer_stride + (p % inner) * inner_stride.
+// One pass over one array. Pencil p: positions i = 0..n-1 at  base(p) + i * es  (floats), each position holding
+// cq(p) float4 of independent channels:
+//   W pass:  p = row y,    base = y * W * C,        es = C,      cq = C/4
+//   H pass:  p = strip s,  base = s * WX * C,       es = W * C,  cq = min(WX, W - s*WX) * C/4
 struct BlurPass {
+    const float* in;
+    float* out;
     int n;                 // length of the blurred axis
     long long es;          // element stride along the blurred axis (floats)
-    int npencil, inner;
-    long long outer_stride, inner_stride;
-    int C;
-    int ntaps;
-    int adjoint;
+    int npencil;
+    long long pencil_stride;   // floats between pencil bases
+    int cq_full;           // float4 per position of a full pencil
+    int cq_last;           // float4 per position of the last pencil
+    int tlg;               // output groups (of 8 positions) per tile
+    int tiles_per;         // tiles per pencil
+    int tpg;               // staged position groups per tile (outputs + halo + slack)
+    int S;                 // float4 per staged position group in shared memory (8*cq + pad)
+    int rp;                // pencils per CTA (narrow pencils are batched so a CTA has ~160 work items)
+    int tapset;
+    int cta_begin;         // first CTA of this pass in the launch
+};
+constexpr int MAX_ITEMS = 12;    // 6 density + 6 appearance factors in one launch
+constexpr int MAX_SETS = 2;      // density taps, colour taps
+// One launch = one pass over up to MAX_ITEMS arrays (large kernel parameters: ~5 KB)
+struct BlurLaunch {
+    int nitems, ntaps, adjoint;
+    BlurPass it[MAX_ITEMS];
+    float k[MAX_SETS][KPAD];         // taps (flipped for the adjoint), zero padded
+    float kraw[MAX_SETS][MAX_TAPS];  // adjoint only: taps in the original order (edge formulas)
 };
 
-__global__ void __launch_bounds__(256) blur_pass_kernel(BlurPass P, const float* __restrict__ in,
-                                                        float* __restrict__ out, const float* __restrict__ taps) {
-    extern __shared__ __align__(128) unsigned char raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ float ks[MAX_TAPS];       // taps (flipped for the adjoint)
-    __shared__ float kcum[MAX_TAPS];     // adjoint only: prefix / suffix sums of the taps
-    __shared__ float ksuf[MAX_TAPS];
-    float* tile = reinterpret_cast<float*>(raw);
+__device__ __forceinline__ void fma4(float4& a, const float k, const float4 x) {
+    a.x = fmaf(k, x.x, a.x); a.y = fmaf(k, x.y, a.y); a.z = fmaf(k, x.z, a.z); a.w = fmaf(k, x.w, a.w);
+}
 
-    const int h = P.ntaps >> 1;
-    const int tiles_per = (P.n + TL - 1) / TL;
-    const int pencil = blockIdx.x / tiles_per;
-    const int t0 = (blockIdx.x - pencil * tiles_per) * TL;
-    const long long base = (long long)(pencil / P.inner) * P.outer_stride + (long long)(pencil % P.inner) * P.inner_stride;
-    const int lo = max(t0 - h, 0), hi = min(t0 + TL + h, P.n);       // staged range [lo, hi)
-    const int span = hi - lo;
-    const int C = P.C;
-    const uint32_t row_bytes = (uint32_t)C * 4u;
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int t = threadIdx.x; t < P.ntaps; t += blockDim.x) ks[t] = P.adjoint ? taps[P.ntaps - 1 - t] : taps[t];
-    __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)span * row_bytes);
-    __syncthreads();
-    if (P.es == C) {                     // contiguous tile: one bulk copy
-        if (threadIdx.x == 0) bulk_g2s(tile, in + base + (long long)lo * P.es, (uint32_t)span * row_bytes, &bar);
-    } else {                             // strided tile: one bulk copy per position
-        for (int i = threadIdx.x; i < span; i += blockDim.x)
-            bulk_g2s(tile + (size_t)i * C, in + base + (long long)(lo + i) * P.es, row_bytes, &bar);
-    }
-    if (P.adjoint && threadIdx.x == 32) {     // tiny serial prefix sums, overlapped with the copy
-        float s = 0.f;
-        for (int t = 0; t < P.ntaps; ++t) { s += taps[t]; kcum[t] = s; }
-        s = 0.f;
-        for (int t = P.ntaps - 1; t >= 0; --t) { s += taps[t]; ksuf[t] = s; }
-    }
-    mbar_wait(&bar, 0);
-    __syncthreads();
-
-    const int ngroups = (min(TL, P.n - t0) + 3) >> 2;         // groups of 4 outputs
-    for (int w = threadIdx.x; w < ngroups * C; w += blockDim.x) {
-        const int c = w % C, gidx = w / C;
-        const int p0 = t0 + gidx * 4;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        // value at absolute position q (forward: replicate; adjoint: zero outside)
-        auto at = [&](int q) -> float {
-            if (P.adjoint) return (q >= 0 && q < P.n) ? tile[(size_t)(q - lo) * C + c] : 0.f;
-            q = min(max(q, 0), P.n - 1);
-            return tile[(size_t)(q - lo) * C + c];
-        };
-        float v0 = at(p0 - h), v1 = at(p0 - h + 1), v2 = at(p0 - h + 2);
-        for (int t = 0; t < P.ntaps; ++t) {
-            const float v3 = at(p0 - h + t + 3);
-            const float kv = ks[t];
-            a0 = fmaf(kv, v0, a0); a1 = fmaf(kv, v1, a1); a2 = fmaf(kv, v2, a2); a3 = fmaf(kv, v3, a3);
-            v0 = v1; v1 = v2; v2 = v3;
-        }
-        float r[4] = {a0, a1, a2, a3};
+// 8 taps kk[0..7] applied to the window (lo = positions w..w+7, hi = w+8..w+15): acc[j] += kk[t] * x[w + j + t]
+__device__ __forceinline__ void tap_block(float4 (&acc)[R_OUT], const float4 (&lo)[8], const float4 (&hi)[8], const float* kk) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int m = p0 + k;
-            if (m >= P.n) break;
-            float v = r[k];
-            if (P.adjoint && (m == 0 || m == P.n - 1)) {      // fold the replicate padding back onto the edge
-                v = 0.f;
-                if (m == 0) {
-                    for (int i = 0; i <= min(h, P.n - 1); ++i) v += tile[(size_t)(i - lo) * C + c] * kcum[h - i];
-                } else {
-                    for (int i = max(P.n - 1 - h, 0); i < P.n; ++i) v += tile[(size_t)(i - lo) * C + c] * ksuf[P.n - 1 - i + h];
-                }
-            }
-            out[base + (long long)m * P.es + c] = v;
+    for (int t = 0; t < 8; ++t) {
+        const float kv = kk[t];
+#pragma unroll
+        for (int j = 0; j < R_OUT; ++j) {
+            const int m = j + t;
+            fma4(acc[j], kv, m < 8 ? lo[m] : hi[m - 8]);
         }
     }
 }
 
-static int launch_pass(const BlurPass& P, const float* in, float* out, const float* taps, cudaStream_t stream) {
-    const int h = P.ntaps >> 1;
-    size_t smem = (size_t)(TL + 2 * h) * P.C * sizeof(float);
-    if (smem > 200 * 1024) return JT_ERR_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(blur_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
-            return JT_ERR_LAUNCH;
-        configured = 200 * 1024;
+__global__ void __launch_bounds__(BL_THREADS) blur_pass_kernel(const __grid_constant__ BlurLaunch M) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float4* tile = reinterpret_cast<float4*>(raw);
+
+    int item = 0;
+    while (item + 1 < M.nitems && (int)blockIdx.x >= M.it[item + 1].cta_begin) ++item;
+    const BlurPass& P = M.it[item];
+    const float* __restrict__ in = P.in;
+    float* __restrict__ out = P.out;
+    const float* kf = M.k[P.tapset];
+    const float* kraw = M.kraw[P.tapset];
+    const int ntaps = M.ntaps, adjoint = M.adjoint;
+    const int cta = blockIdx.x - P.cta_begin;
+    const int h = ntaps >> 1;
+    const int pgroup = cta / P.tiles_per;                             // group of rp pencils
+    const int tidx = cta - pgroup * P.tiles_per;
+    const int t0 = tidx * P.tlg * R_OUT;                              // first output position of the tile
+    const int S = P.S;
+    const int q0 = t0 - h;                                            // absolute position of staged position 0
+    const int npos = P.tpg * 8;
+    const int p_first = pgroup * P.rp;
+    const int np = min(P.rp, P.npencil - p_first);                    // pencils of this CTA
+    const size_t pen_f4 = (size_t)P.tpg * S;                          // float4 per staged pencil
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // bytes that will arrive: forward copies every staged position (clamped source); the adjoint
+        // copies the in-range ones only
+        int cnt = npos;
+        if (adjoint) { const int lo = max(q0, 0), hi = min(q0 + npos, P.n); cnt = max(hi - lo, 0); }
+        uint32_t bytes = 0;
+        for (int r = 0; r < np; ++r) bytes += (uint32_t)cnt * (uint32_t)(p_first + r == P.npencil - 1 ? P.cq_last : P.cq_full) * 16u;
+        mbar_expect_tx(&bar, bytes);
     }
-    const int tiles_per = (P.n + TL - 1) / TL;
+    __syncthreads();
+    // one work item per staged position, or per group of 8 positions where one copy can bring the whole group
+    for (int itx = threadIdx.x; itx < np * npos; itx += blockDim.x) {
+        const int r = itx / npos, it = itx - r * npos;
+        const int pencil = p_first + r;
+        const int cq = pencil == P.npencil - 1 ? P.cq_last : P.cq_full;
+        const long long base = (long long)pencil * P.pencil_stride;
+        const bool contiguous = P.es == (long long)cq * 4;
+        const int g = it >> 3, i = it & 7;
+        const int a0 = q0 + g * 8;
+        float4* dst = tile + r * pen_f4 + (size_t)g * S;
+        if (contiguous && a0 >= 0 && a0 + 8 <= P.n) {
+            if (i == 0) bulk_g2s(dst, in + base + (long long)a0 * P.es, (uint32_t)cq * 128u, &bar);
+            continue;
+        }
+        const int a = a0 + i;
+        if ((a >= 0 && a < P.n) || !adjoint) {
+            const int ac = min(max(a, 0), P.n - 1);
+            bulk_g2s(dst + (size_t)i * cq, in + base + (long long)ac * P.es, (uint32_t)cq * 16u, &bar);
+        } else {
+            for (int c = 0; c < cq; ++c) dst[(size_t)i * cq + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    const int n_out = min(P.tlg * R_OUT, P.n - t0);                   // outputs of this tile (per pencil)
+    const int ngroups = (n_out + R_OUT - 1) / R_OUT;
+    const int nb2 = (ntaps / 16) * 2;                                 // tap blocks processed in pairs
+    const int per_pencil = ngroups * P.cq_full;
+    for (int wx = threadIdx.x; wx < np * per_pencil; wx += blockDim.x) {
+        const int r = wx / per_pencil, w = wx - r * per_pencil;
+        const int pencil = p_first + r;
+        const int cq = pencil == P.npencil - 1 ? P.cq_last : P.cq_full;
+        const int g = w / P.cq_full, c = w - g * P.cq_full;
+        if (c >= cq) continue;                                        // narrower last strip
+        const long long base = (long long)pencil * P.pencil_stride;
+        const float4* ptile = tile + r * pen_f4;
+        // staged position of (output j, tap t) = 8 g + j + t  ->  group g + (j+t)/8, slot (j+t)%8
+        const float4* xp = ptile + (size_t)g * S + c;
+        float4 acc[R_OUT];
+#pragma unroll
+        for (int j = 0; j < R_OUT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 A[8], B[8];
+        auto load8 = [&](float4 (&dst)[8], int grp) {
+            const float4* s = xp + (size_t)grp * S;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = s[i * cq];
+        };
+        load8(A, 0);
+        load8(B, 1);
+        for (int b = 0; b < nb2; b += 2) {
+            tap_block(acc, A, B, kf + 8 * b);
+            load8(A, b + 2);
+            tap_block(acc, B, A, kf + 8 * b + 8);
+            load8(B, b + 3);
+        }
+        for (int t = nb2 * 8; t < ntaps; ++t) {                       // leftover taps (65 taps: one)
+            const float kv = kf[t];
+#pragma unroll
+            for (int j = 0; j < R_OUT; ++j) {
+                const int m = j + t;
+                fma4(acc[j], kv, xp[(size_t)(m >> 3) * S + (m & 7) * cq]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R_OUT; ++j) {
+            const int m = t0 + g * R_OUT + j;
+            if (m >= P.n || g * R_OUT + j >= n_out) break;
+            float4 v = acc[j];
+            if (adjoint && (m == 0 || m == P.n - 1)) {                // fold the replicate padding back onto the edge
+                v = make_float4(0.f, 0.f, 0.f, 0.f);
+                // dy[i] lives at staged position i - q0
+                if (m == 0) {
+                    float ks = 0.f;                                   // sum_{t <= h - i} k[t], built downwards from i = min(h, n-1)
+                    const int i1 = min(h, P.n - 1);
+                    for (int i = i1; i >= 0; --i) {
+                        if (i == i1) { for (int t = 0; t <= h - i; ++t) ks += kraw[t]; }
+                        else ks += kraw[h - i];
+                        const int sp = i - q0;
+                        fma4(v, ks, ptile[(size_t)(sp >> 3) * S + (sp & 7) * cq + c]);
+                    }
+                } else {
+                    float ks = 0.f;                                   // sum_{t >= n-1-i+h} k[t], built upwards from i = n-1-h
+                    const int i0 = max(P.n - 1 - h, 0);
+                    for (int i = i0; i < P.n; ++i) {
+                        if (i == i0) { for (int t = P.n - 1 - i + h; t < ntaps; ++t) ks += kraw[t]; }
+                        else ks += kraw[P.n - 1 - i + h];
+                        const int sp = i - q0;
+                        fma4(v, ks, ptile[(size_t)(sp >> 3) * S + (sp & 7) * cq + c]);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(out + base + (long long)m * P.es + 4 * c) = v;
+        }
+    }
+}
+
+static void plan_pass(BlurPass& P, int ntaps) {
+    // tile length: balance the tiles of a pencil, at most 128 outputs (16 groups) each
+    const int groups = (P.n + R_OUT - 1) / R_OUT;
+    P.tiles_per = (groups + 15) / 16;
+    P.tlg = (groups + P.tiles_per - 1) / P.tiles_per;
+    // staged groups: outputs + halo (ntaps - 1 positions) + the look-ahead of the sliding window (2 groups)
+    P.tpg = P.tlg + (ntaps - 1 + 7) / 8 + 2;
+    // pad every position group so that consecutive work items (c fastest, then output group) of a warp
+    // hit distinct 16-byte bank groups: S = 8 cq + (cq mod 8)  =>  g S + c == g cq + c (mod 8)
+    P.S = 8 * P.cq_full + (P.cq_full & 7);
+    int rp = 160 / (P.tlg * P.cq_full);
+    rp = rp < 1 ? 1 : (rp > 8 ? 8 : rp);
+    while (rp > 1 && (size_t)rp * P.tpg * P.S * 16 > 72 * 1024) --rp;
+    if (rp > P.npencil) rp = P.npencil;
+    P.rp = rp;
+}
+static void row_pass(BlurPass& P, const float* in, float* out, int H, int W, int C) {     // along W
+    P.in = in; P.out = out;
+    P.n = W; P.es = C; P.npencil = H; P.pencil_stride = (long long)W * C; P.cq_full = C / 4; P.cq_last = C / 4;
+}
+static void col_pass(BlurPass& P, const float* in, float* out, int H, int W, int C) {     // along H
+    const int Q = C / 4;
+    int WX = 24 / Q; if (WX < 1) WX = 1; if (WX > W) WX = W;       // strips of WX columns, <= 24 float4 per position
+    P.in = in; P.out = out;
+    P.n = H; P.es = (long long)W * C; P.npencil = (W + WX - 1) / WX; P.pencil_stride = (long long)WX * C;
+    P.cq_full = WX * Q; P.cq_last = (W - (P.npencil - 1) * WX) * Q;
+}
+
+static int launch(BlurLaunch& L, cudaStream_t stream) {
+    if (L.nitems == 0) return JT_OK;
+    size_t smem = 0;
+    int ctas = 0, items_max = 0;
+    for (int i = 0; i < L.nitems; ++i) {
+        BlurPass& P = L.it[i];
+        plan_pass(P, L.ntaps);
+        P.cta_begin = ctas;
+        ctas += ((P.npencil + P.rp - 1) / P.rp) * P.tiles_per;
+        const size_t b = (size_t)P.rp * P.tpg * P.S * 16;
+        smem = b > smem ? b : smem;
+        const int items = P.rp * P.tlg * P.cq_full;
+        items_max = items > items_max ? items : items_max;
+    }
+    if (smem > 220 * 1024) return JT_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(blur_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+            return JT_ERR_LAUNCH;
+        configured = true;
+    }
+    // block size: the work items (output groups x float4 columns) of the widest pass split evenly over the fewest rounds
+    const int rounds = (items_max + BL_THREADS - 1) / BL_THREADS;
+    int threads = (((items_max + rounds - 1) / rounds + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
     g_launches += 1;
-    blur_pass_kernel<<<P.npencil * tiles_per, 256, smem, stream>>>(P, in, out, taps);
-    return JT_OK;
+    blur_pass_kernel<<<ctas, threads, smem, stream>>>(L);
+    return cudaGetLastError() == cudaSuccess ? JT_OK : JT_ERR_LAUNCH;
 }
 
 }  // namespace jt
 
 using namespace jt;
 
-// Blur a channel-last [H][W][C] array. axes bit0: along W, bit1: along H (a line
-// factor [L][C] is H=L, W=1, axes=2). tmp is required when both axes are set.
-// Forward order is W then H (bateRF.py:29-36); the adjoint runs H then W.
-extern "C" int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* taps,
+// Blur up to 12 channel-last arrays ([H][W][C] each) with two launches (one per pass): all W passes (and the
+// single pass of arrays with one blurred axis) first, then the H passes of the two-axis arrays.
+// h_dims = {H, W, C, axes} per array; axes bit0: along W, bit1: along H (a line factor [L][C] is H=L, W=1,
+// axes=2). Forward order is W then H (bateRF.py:29-36); the adjoint runs H then W. h_tmp[i] is required when
+// axes == 3. Array i uses tap set h_tapset[i] of h_taps [nsets][ntaps] (host).
+extern "C" int jt_blur_multi(int n_arrays, const void* const* h_in, void* const* h_out, void* const* h_tmp,
+                             const int* h_dims, const int* h_tapset, const float* h_taps, int nsets, int ntaps,
+                             int adjoint, cudaStream_t stream) {
+    JT_CHECK_ARG(n_arrays >= 0 && n_arrays <= MAX_ITEMS && nsets >= 1 && nsets <= MAX_SETS);
+    if (n_arrays == 0) return JT_OK;
+    JT_CHECK_ARG(h_in && h_out && h_dims && h_taps);
+    JT_CHECK_ARG(ntaps >= 1 && (ntaps & 1) == 1 && ntaps <= MAX_TAPS);
+    static thread_local BlurLaunch A, B;             // first / second pass
+    for (BlurLaunch* L : {&A, &B}) {
+        L->nitems = 0; L->ntaps = ntaps; L->adjoint = adjoint;
+        for (int s = 0; s < MAX_SETS; ++s) {
+            const float* t = h_taps + (size_t)(s < nsets ? s : 0) * ntaps;
+            for (int i = 0; i < KPAD; ++i) L->k[s][i] = i < ntaps ? (adjoint ? t[ntaps - 1 - i] : t[i]) : 0.f;
+            for (int i = 0; i < MAX_TAPS; ++i) L->kraw[s][i] = i < ntaps ? t[i] : 0.f;
+        }
+    }
+    for (int i = 0; i < n_arrays; ++i) {
+        const float* in = static_cast<const float*>(h_in[i]);
+        float* out = static_cast<float*>(h_out[i]);
+        float* tmp = h_tmp ? static_cast<float*>(h_tmp[i]) : nullptr;
+        const int H = h_dims[4 * i], W = h_dims[4 * i + 1], C = h_dims[4 * i + 2], axes = h_dims[4 * i + 3];
+        const int set = h_tapset ? h_tapset[i] : 0;
+        JT_CHECK_ARG(in && out && H >= 1 && W >= 1 && C >= 4 && (C & 3) == 0 && axes >= 1 && axes <= 3);
+        JT_CHECK_ARG(set >= 0 && set < nsets);
+        JT_CHECK_ARG(axes != 3 || tmp);
+        JT_CHECK_ARG(in != out);
+        JT_CHECK_ARG(!(axes & 1) || W >= 2);
+        JT_CHECK_ARG(!(axes & 2) || H >= 2);
+        JT_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(tmp) & 15) == 0);
+        BlurPass& a = A.it[A.nitems];
+        a.tapset = set;
+        if (axes == 1) { row_pass(a, in, out, H, W, C); A.nitems++; }
+        else if (axes == 2) { col_pass(a, in, out, H, W, C); A.nitems++; }
+        else {
+            BlurPass& b = B.it[B.nitems];
+            b.tapset = set;
+            if (!adjoint) { row_pass(a, in, tmp, H, W, C); col_pass(b, tmp, out, H, W, C); }
+            else { col_pass(a, in, tmp, H, W, C); row_pass(b, tmp, out, H, W, C); }
+            A.nitems++; B.nitems++;
+        }
+    }
+    if (int rc = launch(A, stream)) return rc;
+    return launch(B, stream);
+}
+
+// One array (see jt_blur_multi).
+extern "C" int jt_blur_cl(const float* in, float* out, float* tmp, int H, int W, int C, const float* h_taps,
                           int ntaps, int axes, int adjoint, cudaStream_t stream) {
-    JT_CHECK_ARG(in && out && taps && H >= 1 && W >= 1 && C >= 4 && (C & 3) == 0);
-    JT_CHECK_ARG(ntaps >= 1 && (ntaps & 1) == 1 && ntaps <= MAX_TAPS && axes >= 1 && axes <= 3);
-    JT_CHECK_ARG(axes != 3 || tmp);
-    JT_CHECK_ARG(in != out);
-    JT_CHECK_ARG(!(axes & 1) || W >= 2);
-    JT_CHECK_ARG(!(axes & 2) || H >= 2);
-    BlurPass pw{W, (long long)C, H, 1, (long long)W * C, 0, C, ntaps, adjoint};           // rows
-    BlurPass ph{H, (long long)W * C, W, W, 0, (long long)C, C, ntaps, adjoint};           // columns
-    int rc = JT_OK;
-    if (axes == 1) rc = launch_pass(pw, in, out, taps, stream);
-    else if (axes == 2) rc = launch_pass(ph, in, out, taps, stream);
-    else if (!adjoint) { rc = launch_pass(pw, in, tmp, taps, stream); if (!rc) rc = launch_pass(ph, tmp, out, taps, stream); }
-    else { rc = launch_pass(ph, in, tmp, taps, stream); if (!rc) rc = launch_pass(pw, tmp, out, taps, stream); }
-    if (rc) return rc;
-    JT_RETURN_LAUNCH();
+    const void* ins[1] = {in};
+    void* outs[1] = {out};
+    void* tmps[1] = {tmp};
+    const int dims[4] = {H, W, C, axes};
+    const int set[1] = {0};
+    JT_CHECK_ARG(h_taps);
+    return jt_blur_multi(1, ins, outs, tmps, dims, set, h_taps, 1, ntaps, adjoint, stream);
 }

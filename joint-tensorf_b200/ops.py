@@ -251,14 +251,75 @@ def head_bwd_tc(dout, feat, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, 
 
 
 # ------------------------------------------------------------------ K5
+def host_taps(kernel):
+    """Blur taps as a host float array (they travel in the kernel parameters / constant bank).
+    `B200_VMSplit.get_kernel` computes the taps on the host and attaches them to the device tensor it
+    returns (`_jt_host`); a foreign tensor costs one device->host copy."""
+    if isinstance(kernel, (list, tuple)):
+        vals = list(kernel)
+    else:
+        vals = getattr(kernel, "_jt_host", None)
+        if vals is None:
+            vals = kernel.detach().reshape(-1).float().cpu().tolist()
+    return floats(vals), len(vals)
+
+
 def blur_cl(x_phys, h, w, c, taps, axes, adjoint):
-    """x_phys: contiguous fp32 buffer holding h*w*c floats, interpreted as [h][w][c]."""
+    """x_phys: contiguous fp32 buffer holding h*w*c floats, interpreted as [h][w][c]; taps = host_taps(...)."""
     out = torch.empty_like(x_phys)
     tmp = torch.empty_like(x_phys) if axes == 3 else None
+    h_taps, ntaps = taps
     with TIMER.span("blur_adj" if adjoint else "blur_fwd"):
-        check(_lib.lib().jt_blur_cl(_p(x_phys), _p(out), _p(tmp), h, w, c, _p(taps), taps.numel(), axes,
+        check(_lib.lib().jt_blur_cl(_p(x_phys), _p(out), _p(tmp), h, w, c, h_taps, ntaps, axes,
                                     int(adjoint), _stream()), "jt_blur_cl")
     return out
+
+
+def blur_multi(arrays, metas, tapsets, adjoint):
+    """arrays: contiguous fp32 buffers; metas[i] = (h, w, c, axes, tapset); tapsets: list of host tap lists of
+    equal length (<= 2). One C-ABI call, two launches (csrc/blur.cu). Returns the blurred buffers."""
+    outs = [torch.empty_like(a) for a in arrays]
+    tmps = [torch.empty_like(a) if m[3] == 3 else None for a, m in zip(arrays, metas)]
+    ntaps = len(tapsets[0])
+    assert all(len(t) == ntaps for t in tapsets)
+    flat = floats([v for t in tapsets for v in t])
+    dims = ints([v for m in metas for v in m[:4]])
+    sets = ints([m[4] for m in metas])
+    with TIMER.span("blur_adj" if adjoint else "blur_fwd"):
+        check(_lib.lib().jt_blur_multi(len(arrays), ptrs([a.data_ptr() for a in arrays]),
+                                       ptrs([o.data_ptr() for o in outs]), ptrs([_p(t) for t in tmps]), dims, sets,
+                                       flat, len(tapsets), ntaps, int(adjoint), _stream()), "jt_blur_multi")
+    return outs
+
+
+class BlurGroup(torch.autograd.Function):
+    """All blurred factors of a step as ONE autograd node: forward = two launches (W passes, then H passes) over
+    up to 12 arrays, backward = two launches of the adjoint. `metas[i] = (hq, wq, axes, tapset)` per factor
+    (see BlurFactor for the (hq, wq) re-interpretation); `tapsets` = host tap lists (density, colour)."""
+
+    @staticmethod
+    def forward(ctx, metas, tapsets, *factors):
+        xs, full = [], []
+        for x, (hq, wq, axes, ts) in zip(factors, metas):
+            _need_cuda(x, "factor")
+            xp = phys_cl(x)
+            c = xp.shape[2]
+            assert xp.shape[0] * xp.shape[1] == hq * wq
+            xs.append(xp)
+            full.append((hq, wq, c, axes, ts))
+        ys = blur_multi(xs, full, tapsets, 0)
+        ctx.meta = (full, tapsets, [tuple(xp.shape) for xp in xs])
+        return tuple(y.view(1, m[0], m[1], m[2]).permute(0, 3, 1, 2) for y, m in zip(ys, full))
+
+    @staticmethod
+    def backward(ctx, *gys):
+        full, tapsets, shapes = ctx.meta
+        idx = [i for i, g in enumerate(gys) if g is not None and ctx.needs_input_grad[2 + i]]
+        gxs = blur_multi([phys_cl(gys[i]) for i in idx], [full[i] for i in idx], tapsets, 1) if idx else []
+        out = [None] * len(gys)
+        for i, gx in zip(idx, gxs):
+            out[i] = gx.view(1, *shapes[i]).permute(0, 3, 1, 2)
+        return (None, None, *out)
 
 
 class BlurFactor(torch.autograd.Function):
@@ -276,17 +337,16 @@ class BlurFactor(torch.autograd.Function):
         xp = phys_cl(x)
         c = xp.shape[2]
         assert xp.shape[0] * xp.shape[1] == hq * wq
-        y = blur_cl(xp, hq, wq, c, taps, axes, 0)
-        ctx.save_for_backward(taps)
-        ctx.meta = (tuple(xp.shape), hq, wq, c, axes)
+        ht = host_taps(taps)
+        y = blur_cl(xp, hq, wq, c, ht, axes, 0)
+        ctx.meta = (tuple(xp.shape), hq, wq, c, axes, ht)
         return y.view(1, hq, wq, c).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
-        (taps,) = ctx.saved_tensors
-        shape, hq, wq, c, axes = ctx.meta
+        shape, hq, wq, c, axes, ht = ctx.meta
         gp = phys_cl(gy)
-        gx = blur_cl(gp, hq, wq, c, taps, axes, 1)
+        gx = blur_cl(gp, hq, wq, c, ht, axes, 1)
         return gx.view(1, *shape).permute(0, 3, 1, 2), None, None, None, None
 
 

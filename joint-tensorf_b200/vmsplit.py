@@ -335,7 +335,10 @@ class B200_VMSplit(torch.nn.Module):
 
     # ---------------------------------------------------------------- K5 API
     def get_kernel(self, opt, c2f_mode, c2f_parameter, c2f_kernel_size=25):
-        """BatBase.get_kernel (batBase.py:13-25): taps on the device, computed on the host."""
+        """BatBase.get_kernel (batBase.py:13-25). The taps are computed on the host and STAY there: the blur
+        kernels take them through their launch parameters (constant bank), so the per-step host->device copy of
+        the reference (a stream synchronisation for pageable memory) is gone and the host keeps running ahead
+        of the GPU. Returns a CPU tensor carrying the tap list as `_jt_host`."""
         t = self._blur_scale * float(c2f_parameter)
         if c2f_mode == "uniform-gaussian":
             k = gaussian_taps(t, c2f_kernel_size)
@@ -343,13 +346,15 @@ class B200_VMSplit(torch.nn.Module):
             k = average_taps(t, c2f_kernel_size)
         else:
             raise RuntimeError(f"invalid c2f_mode {c2f_mode}")
-        return k.to(device=self.device, dtype=torch.float32)
+        kd = k.to(dtype=torch.float32)
+        kd._jt_host = kd.reshape(-1).tolist()
+        return kd
 
     def convolute_line(self, kernel, line):
-        return ops.BlurFactor.apply(line, kernel.reshape(-1).contiguous(), line.shape[2], 1, 2)
+        return ops.BlurFactor.apply(line, kernel, line.shape[2], 1, 2)
 
     def convolute_plane(self, kernel, plane, H, W):
-        return ops.BlurFactor.apply(plane, kernel.reshape(-1).contiguous(), int(H), int(W), 3)
+        return ops.BlurFactor.apply(plane, kernel, int(H), int(W), 3)
 
     def _blurred(self, planes, lines, kernel):
         """All six factors of one group, blurred (bateRF.py:64-78 / 105-118)."""
@@ -361,6 +366,39 @@ class B200_VMSplit(torch.nn.Module):
             bp.append(self.convolute_plane(kernel, planes[i], self._grid[m0], self._grid[m1]))
             bl.append(self.convolute_line(kernel, lines[i]))
         return bp, bl
+
+    def _blurred_all(self, kernel_density, kernel_color):
+        """The 12 factors of a forward call, blurred by one autograd node / two launches per direction
+        (bateRF.py:64-78 and 105-118 run 18 conv1d calls with their pads and permutes)."""
+        groups = [(self.density_plane, self.density_line, kernel_density), (self.app_plane, self.app_line, kernel_color)]
+        active = [(p, l, k) for p, l, k in groups if k is not None]
+        if not active:
+            return list(self.density_plane), list(self.density_line), list(self.app_plane), list(self.app_line)
+        tapsets, metas, factors = [], [], []
+        for p, l, k in active:
+            ht = getattr(k, "_jt_host", None)
+            tapsets.append(list(ht) if ht is not None else k.detach().reshape(-1).float().cpu().tolist())
+        if len(tapsets) == 2 and len(tapsets[0]) != len(tapsets[1]):      # different tap counts: one node per group
+            dp, dl = self._blurred(self.density_plane, self.density_line, kernel_density)
+            ap, al = self._blurred(self.app_plane, self.app_line, kernel_color)
+            return dp, dl, ap, al
+        for s, (p, l, k) in enumerate(active):
+            for i in range(3):
+                m0, m1 = MAT_MODE[i]
+                factors.append(p[i])
+                metas.append((self._grid[m0], self._grid[m1], 3, s))
+            for i in range(3):
+                factors.append(l[i])
+                metas.append((l[i].shape[2], 1, 2, s))
+        outs = list(ops.BlurGroup.apply(metas, tapsets, *factors))
+        res = []
+        for p, l, k in groups:
+            if k is None:
+                res += [list(p), list(l)]
+            else:
+                res += [outs[:3], outs[3:6]]
+                outs = outs[6:]
+        return res[0], res[1], res[2], res[3]
 
     # ---------------------------------------------------------------- K2 API
     def compute_densityfeature(self, xyz_sampled, kernel=None, c2f_mode=None, interp_mode="bilinear"):
@@ -450,8 +488,7 @@ class B200_VMSplit(torch.nn.Module):
                                            sum(self.app_n_comp) == 144):
             cfg.head = "tc"
 
-        dp, dl = self._blurred(self.density_plane, self.density_line, self.kernel_density)
-        ap, al = self._blurred(self.app_plane, self.app_line, self.kernel_color)
+        dp, dl, ap, al = self._blurred_all(self.kernel_density, self.kernel_color)
         head = self.renderModule.head_params() if self.renderModule is not None else []
         return VMRender.apply(cfg, center.reshape(-1, 3), ray_dir.reshape(-1, 3), aux, *dp, *dl, *ap, *al,
                               self.basis_mat.weight, *head)

@@ -463,6 +463,67 @@ def own_arm(args):
         render = {"ms_per_frame": fms, "rays_per_s": n_pix / (fms * 1e-3), "frame": "800x800", "rays_per_call": chunk,
                   "finite": bool(torch.isfinite(img).all())}
 
+    # next rows of SURVEY 8f, timed after everything above because the optimiser changes the parameters:
+    # 8f-2 a full training iteration = the step above + density_L1 regulariser (Blender weight 8e-5, TV weights 0,
+    # bat_blender_VM.yaml:134-139) + Adam update of every parameter; 8f-3 the between-step maintenance ops.
+    extras = None
+    if rank == 0 and not args.no_breakdown:
+        from joint_tensorf_b200.sweeps import FusedAdam
+        fused = FusedAdam(model.get_optparam_groups(0.02, 1e-3) + [{"params": [se3_refine], "lr": 1e-3}],
+                          betas=(0.9, 0.99))
+        decay = 0.1 ** (1 / 30000)
+
+        def train_step():
+            step(pix_d, tgt_d, reduce=False)
+            model.regularize_(8e-5, 0.0, 0.0)
+            fused.step()
+            for grp in fused.param_groups:
+                grp["lr"] *= decay
+
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        ms_train = timed(train_step, 5) / 5
+        ops.TIMER.enabled = True
+        model.regularize_(8e-5, 1.0, 1.0)
+        fused.step()
+        ops.TIMER.summary()
+        for _ in range(5):
+            flush.fill_(1.0)
+            model.regularize_(8e-5, 1.0, 1.0)            # all three terms: the LLFF configuration (weights 10.0)
+            fused.step()
+        sw = {k: round(v[0] / 5, 4) for k, v in ops.TIMER.summary().items()}
+        n_par = sum(p.numel() for grp in fused.param_groups for p in grp["params"])
+        # arrays the three-term sweep touches: density planes + lines (L1, TV) and appearance planes (TV)
+        n_sw = sum(p.numel() for p in [*model.density_plane, *model.density_line, *model.app_plane])
+        # algorithmic bytes: Adam reads p, g, m, v and writes p, m, v; the value sweep reads x once; the gradient
+        # sweep reads x and read-modify-writes g
+        sweep_bytes = {"adam": 28 * n_par, "reg_values": 4 * n_sw, "reg_grads": 12 * n_sw}
+        extras = {"train_step_ms": round(ms_train, 4),
+                  "train_step_what": "step + density_L1 (value + gradient sweep) + fused Adam over all parameters",
+                  "sweep_ms": sw,
+                  "sweep_gbs": {k: round(sweep_bytes[k] / (sw[k] * 1e-3) / 1e9, 1) for k in sweep_bytes if sw.get(k)},
+                  "sweep_bytes": sweep_bytes, "hbm_peak_gbs": hbm_peak}
+        # maintenance: dense alpha on 200^3 (tensorf.py update_alphamask), mask build, 150^3 -> 300^3 upsample
+        model.kernel_density, model.c2f_mode = None, None
+        kw2, _ = jt.synth.config(args.workload)
+        kw2 = dict(kw2)
+        kw2.pop("gridSize")
+        aabb2 = torch.tensor(kw2.pop("aabb"))
+        mt = None
+        for rep in range(2):                          # rep 0 warms up, rep 1 is measured
+            ops.TIMER.summary()
+            a_zyx = model._dense_alpha_zyx([200, 200, 200])
+            ops.alpha_mask_build(a_zyx, model.alphaMask_thres)
+            small = jt.B200_VMSplit(aabb2, [150, 150, 150], dev, **kw2)
+            small.upsample_volume_grid([300, 300, 300])
+            del small
+            mt = ops.TIMER.summary()
+        ops.TIMER.enabled = False
+        extras["maintenance_ms"] = {"dense_alpha_200^3": round(mt["field_alpha"][0], 4),
+                                    "maxpool5_threshold_pack_200^3": round(mt["alpha_mask_build"][0], 4),
+                                    "upsample_150^3_to_300^3_all_factors": round(mt["resize_bilinear"][0], 4)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, sec, cores = time_cpu_port(args.workload, args.cpu_rays, 2, 1, args.blur)
@@ -513,6 +574,8 @@ def own_arm(args):
             line["cpu_baseline"] = cpu
         if aten is not None:
             line["aten_gpu_baseline"] = aten
+        if extras is not None:
+            line["next_rows"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

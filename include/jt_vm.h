@@ -245,6 +245,52 @@ int jt_pose_rays_bwd(const float* se3, const int* view_idx, const float* base, i
                      int center_shift, int detach_shift, float near_plane, const float* d_center, const float* d_ray,
                      float* scratch12, float* d_se3, float* d_pose, cudaStream_t stream);
 
+/* ---- per-step full-factor sweeps (next row) ------ */
+/* The regularisers model/tensorf.py:126-130 evaluates every training step:
+ *   density_L1 (tensoRF.py:212-216), TV_loss_density / TV_loss_app (tensoRF.py:218-228) with
+ *   TVLoss (tensorBase.py:16-41; weight 1, batch 1, the 1e-2 factor of TV_loss_* included).
+ * Arrays are channel-last [H][W][C] fp32 buffers (h_x: HOST array of n_arrays <= 12 device pointers,
+ * h_dims = {H, W, C} per array; a line factor is H = L, W = 1). h_term[i]: 0 = no TV, 1 = TV summed into
+ * TV_density, 2 = into TV_app; h_l1[i] != 0: mean|x| summed into L1.
+ * sums_ws: 36 doubles of scratch; out3 = {L1, TV_density, TV_app}. One sweep: every element read once. */
+int jt_reg_values(int n_arrays, const void* const* h_x, const int* h_dims, const int* h_term, const int* h_l1,
+                  double* sums_ws, float* out3, cudaStream_t stream);
+/* Their autograd in one sweep: h_g[i] += d/dx ( c0*L1 + c1*TV_density + c2*TV_app ), c_k = h_coef3[k]
+ * (host weights, e.g. opt.loss_weight.*) times up3[k] (optional DEVICE upstream gradients, NULL = 1).
+ * Arrays whose host weight is zero are skipped. sign(0) = 0 as in ATen's abs backward. */
+int jt_reg_grads(int n_arrays, const void* const* h_x, void* const* h_g, const int* h_dims, const int* h_term,
+                 const int* h_l1, const float* h_coef3, const float* up3, cudaStream_t stream);
+/* torch.optim.Adam (model/tensorf.py:474-475: betas (0.9, 0.99), eps 1e-8, no weight decay / amsgrad) for all
+ * parameter tensors of a step in ONE launch per 32 tensors (the reference's foreach path makes ~6 passes over
+ * every tensor). Tensor i: p, g, exp_avg m, exp_avg_sq v (dense fp32 buffers of h_numel[i] elements sharing one
+ * physical layout), learning rate h_lr[i] (already decayed by the host, tensorf.py:431-436) and step count
+ * h_step[i] >= 1 (the value AFTER this step's increment). g is multiplied by grad_scale first (1/world_size
+ * after a summing all-reduce) and is zeroed in the same pass when zero_grad != 0. */
+int jt_adam_multi(int n_tensors, void* const* h_p, void* const* h_g, void* const* h_m, void* const* h_v,
+                  const long long* h_numel, const double* h_lr, const int* h_step, double beta1, double beta2,
+                  double eps, double grad_scale, int zero_grad, cudaStream_t stream);
+
+/* ---- field maintenance between steps (next row) -- */
+/* BatBase.compute_alpha (batBase.py:27-42) and TensorBase.getDenseAlpha (tensorBase.py:618-633):
+ * alpha = 1 - exp(-feature2density(sigma_feature(p)) * length), 0 where the occupancy mask rejects p.
+ * xyz != NULL: n_points explicit world-space points [n][3] -> alpha [n].
+ * xyz == NULL: the dense grid p = aabb0*(1-s) + aabb1*s with s from the device tables lin_x/y/z
+ *   (torch.linspace(0, 1, g), h_grid3 = {gx, gy, gz}); alpha is written in [gz][gy][gx] order (the layout
+ *   updateAlphaMask pools, tensorBase.py:639-640). Factors: the (blurred, if a blur is cached) density factors. */
+int jt_field_alpha(const void* const* h_factors, const int* h_dims, const float* h_geom, const float* xyz,
+                   long long n_points, const float* lin_x, const float* lin_y, const float* lin_z, const int* h_grid3,
+                   const uint32_t* mask_bits, const int* h_mask_dims, const float* h_mask_geom, float density_shift,
+                   int act, float length, float* alpha, cudaStream_t stream);
+/* The rest of updateAlphaMask (tensorBase.py:639-657): clamp(alpha, 0, 1) -> max_pool3d(kernel 5, pad 2, stride 1)
+ * -> >= thres, on alpha [D][H][W]. Outputs: vol [D][H][W] floats {0,1} (AlphaGridMask.alpha_volume), bits = the same
+ * bit-packed ((W*H*D+31)/32 words, layout of MaskGeom), stats7 = {min_x, max_x, min_y, max_y, min_z, max_z, count}
+ * of the kept voxels (the new aabb is the grid position of those indices). tmp: W*H*D floats. */
+int jt_alpha_mask_build(const float* alpha, int W, int H, int D, float thres, float* tmp, float* vol, uint32_t* bits,
+                        int* stats7, cudaStream_t stream);
+/* F.interpolate(mode="bilinear", align_corners=True) of one factor (up_sampling_VM, tensoRF.py:274-287) on the
+ * channel-last layout: in [H][W][C] -> out [H2][W2][C]; a line factor is W = W2 = 1. */
+int jt_resize_bilinear_cl(const float* in, int H, int W, int C, float* out, int H2, int W2, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libjt_vm.so")
 
-_P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_P, _I, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
 
 # name -> argtypes; mirrors include/jt_vm.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
@@ -38,6 +38,12 @@ SIGNATURES = {
     "jt_blur_multi": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "jt_pose_rays_fwd": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P],
     "jt_pose_rays_bwd": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
+    "jt_reg_values": [_I, _P, _P, _P, _P, _P, _P, _P],
+    "jt_reg_grads": [_I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "jt_field_alpha": [_P, _P, _P, _P, ctypes.c_longlong, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _P, _P],
+    "jt_alpha_mask_build": [_P, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    "jt_resize_bilinear_cl": [_P, _I, _I, _I, _P, _I, _I, _P],
+    "jt_adam_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _P],
 }
 
 _lib = None
@@ -87,6 +93,14 @@ def floats(vals):
 
 def ints(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def doubles(vals):
+    return (ctypes.c_double * len(vals))(*[float(v) for v in vals])
+
+
+def longlongs(vals):
+    return (ctypes.c_longlong * len(vals))(*[int(v) for v in vals])
 
 
 def ptrs(vals):

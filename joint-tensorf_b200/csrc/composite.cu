@@ -12,23 +12,10 @@
 // samples have sigma = 0 in the reference, i.e. alpha = 0 and a factor
 // 1 - 0 + 1e-10 == 1.0f in the cumprod, so skipping them is exact.
 #include "jt_common.cuh"
+#include "vm_taps.cuh"
 #include "../../include/jt_vm.h"
 
 namespace jt {
-
-__device__ __forceinline__ float density_act(float x, int act) {
-    // act 0: softplus (beta 1, threshold 20; ATen softplus), act 1: relu. x already includes the shift.
-    if (act == 0) return x > 20.0f ? x : log1pf(expf(x));
-    return fmaxf(x, 0.0f);
-}
-__device__ __forceinline__ float density_act_grad(float x, int act) {
-    if (act == 0) {
-        if (x > 20.0f) return 1.0f;
-        float z = expf(x);
-        return z / (z + 1.0f);
-    }
-    return x > 0.0f ? 1.0f : 0.0f;
-}
 
 // ------------------------------------------------------------------ forward, pass A
 // per ray: sigma -> alpha -> T (exclusive product scan) -> weight; accumulates acc

@@ -13,6 +13,7 @@
 // reference's bit for bit. The jitter (torch RNG) and the NDC depth table
 // (torch.linspace) are inputs, never recomputed here.
 #include "jt_common.cuh"
+#include "vm_taps.cuh"
 #include "../../include/jt_vm.h"
 
 namespace jt {
@@ -62,34 +63,6 @@ __device__ __forceinline__ bool point_in_box(const RaySetup& s, const Geom& g, f
         ok = ok && !((g.a0[a] > p[a]) || (p[a] > g.a1[a]));
     }
     return ok;
-}
-
-// grid_sample(volume, trilinear, align_corners=True, zeros) > 0 for a {0,1}
-// volume  <=>  some in-range corner with a set bit has three positive 1-D
-// weights (all 8 terms are non-negative). Index arithmetic follows ATen's
-// scalar path ((u + 1) / 2) * (size - 1) with separately rounded ops.
-__device__ __forceinline__ bool mask_keep(const MaskGeom& m, const float p[3]) {
-    int i0[3];
-    bool frac[3];
-    const int size[3] = {m.W, m.H, m.D};
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        float u = __fsub_rn(__fmul_rn(__fsub_rn(p[a], m.a0[a]), m.inv[a]), 1.0f);
-        float x = __fmul_rn(__fdiv_rn(__fadd_rn(u, 1.0f), 2.0f), (float)(size[a] - 1));
-        float xf = floorf(x);
-        frac[a] = (x - xf) > 0.0f;                 // weight of the +1 corner is positive
-        i0[a] = (int)fminf(fmaxf(xf, -2.0f), (float)size[a]);
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-        if ((dx && !frac[0]) || (dy && !frac[1]) || (dz && !frac[2])) continue;
-        int x = i0[0] + dx, y = i0[1] + dy, z = i0[2] + dz;
-        if (x < 0 || x >= m.W || y < 0 || y >= m.H || z < 0 || z >= m.D) continue;
-        long long n = ((long long)z * m.H + y) * m.W + x;
-        if ((m.bits[n >> 5] >> (n & 31)) & 1u) return true;
-    }
-    return false;
 }
 
 // ---------------------------------------------------------------- dense variant (API parity)
@@ -198,22 +171,6 @@ __global__ void march_fill_kernel(const float* __restrict__ ro, const float* __r
         }
         base += __popc(b);
     }
-}
-
-static Geom make_geom(const float* h) {
-    Geom g;
-    for (int a = 0; a < 3; ++a) { g.a0[a] = h[a]; g.a1[a] = h[3 + a]; g.inv[a] = h[6 + a]; }
-    g.step = h[9]; g.near_ = h[10]; g.far_ = h[11];
-    return g;
-}
-static MaskGeom make_mask(const uint32_t* bits, const int* dims, const float* hg) {
-    MaskGeom m{};
-    m.bits = bits;
-    if (bits) {
-        m.W = dims[0]; m.H = dims[1]; m.D = dims[2];
-        for (int a = 0; a < 3; ++a) { m.a0[a] = hg[a]; m.inv[a] = hg[3 + a]; }
-    }
-    return m;
 }
 
 }  // namespace jt

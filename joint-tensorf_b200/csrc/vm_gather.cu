@@ -16,45 +16,10 @@
 // operations.
 #include <stdlib.h>
 #include "jt_common.cuh"
+#include "vm_taps.cuh"
 #include "../../include/jt_vm.h"
 
 namespace jt {
-
-__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
-__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-__device__ __forceinline__ float4 f4_lerp2(float4 a, float wa, float4 b, float wb) {
-    return make_float4(a.x * wa + b.x * wb, a.y * wa + b.y * wb, a.z * wa + b.z * wb, a.w * wa + b.w * wb);
-}
-__device__ __forceinline__ float4 f4_bilin(float4 a, float wa, float4 b, float wb, float4 c, float wc, float4 d, float wd) {
-    return make_float4(a.x * wa + b.x * wb + c.x * wc + d.x * wd, a.y * wa + b.y * wb + c.y * wc + d.y * wd,
-                       a.z * wa + b.z * wb + c.z * wc + d.z * wd, a.w * wa + b.w * wb + c.w * wc + d.w * wd);
-}
-
-struct PlaneTaps {
-    const float *p00, *p10, *p01, *p11, *l0, *l1;
-    size_t o00, o10, o01, o11, ol0, ol1;     // element offsets (shared by value and gradient buffers)
-    float w00, w10, w01, w11;
-    Tap tx, ty, tl;
-};
-
-__device__ __forceinline__ PlaneTaps plane_taps(const Factors& F, int i, const float u[3]) {
-    PlaneTaps t;
-    t.tx = make_tap(u[mat0(i)], F.W[i]);
-    t.ty = make_tap(u[mat1(i)], F.H[i]);
-    t.tl = make_tap(u[vecm(i)], F.L[i]);
-    const size_t C = F.C[i];
-    size_t r0 = (size_t)t.ty.i0 * F.W[i], r1 = (size_t)t.ty.i1 * F.W[i];
-    t.o00 = (r0 + t.tx.i0) * C; t.o10 = (r0 + t.tx.i1) * C;
-    t.o01 = (r1 + t.tx.i0) * C; t.o11 = (r1 + t.tx.i1) * C;
-    t.ol0 = (size_t)t.tl.i0 * C; t.ol1 = (size_t)t.tl.i1 * C;
-    t.p00 = F.plane[i] + t.o00; t.p10 = F.plane[i] + t.o10;
-    t.p01 = F.plane[i] + t.o01; t.p11 = F.plane[i] + t.o11;
-    t.l0 = F.line[i] + t.ol0; t.l1 = F.line[i] + t.ol1;
-    t.w00 = t.tx.w0 * t.ty.w0; t.w10 = t.tx.w1 * t.ty.w0;     // nw, ne
-    t.w01 = t.tx.w0 * t.ty.w1; t.w11 = t.tx.w1 * t.ty.w1;     // sw, se
-    return t;
-}
 
 // APP == false: out[e] = sum_i sum_c P_ic * L_ic               (density feature)
 // APP == true : out[e][off_i + c] = P_ic * L_ic                (appearance components, before basis_mat)

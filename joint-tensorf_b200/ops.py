@@ -434,3 +434,55 @@ class Linear(torch.autograd.Function):
         gb = torch.zeros((n,), device=gy.device) if has_b else None
         gemm_tn(g, ldy, xp, ldx, None, m, n, k, gw, k, gb, name="basis_bwd_w")
         return gx[:m, :k], gw, gb
+
+
+# ------------------------------------------------------------------ field maintenance (section 8f-3)
+def field_alpha(fs, geom, shift, act, length, xyz=None, lin=None, grid=None, mask=None):
+    """alpha at explicit points (xyz [n,3]) or on the dense grid (lin = 3 device linspace tables, grid = (gx,gy,gz);
+    result [gz,gy,gx]). fs: FactorSet of the density factors."""
+    mb, md, mg = (mask.bits, mask.h_dims, mask.h_geom) if mask is not None else (None, None, None)
+    if xyz is not None:
+        _need_cuda(xyz, "xyz")
+        xyz = xyz.reshape(-1, 3).contiguous().float()
+        n = xyz.shape[0]
+        out = torch.empty((n,), device=xyz.device)
+        lx = ly = lz = None
+        g3 = None
+    else:
+        lx, ly, lz = lin
+        _need_cuda(lx, "linspace table")
+        n = 0
+        out = torch.empty((grid[2], grid[1], grid[0]), device=lx.device)
+        g3 = ints(grid)
+    with TIMER.span("field_alpha"):
+        check(_lib.lib().jt_field_alpha(fs.ptrs, fs.dims, geom, _p(xyz), n, _p(lx), _p(ly), _p(lz), g3, _p(mb), md, mg,
+                                        float(shift), int(act), float(length), _p(out), _stream()), "jt_field_alpha")
+    return out
+
+
+def alpha_mask_build(alpha_zyx, thres):
+    """alpha [D,H,W] -> (vol [D,H,W] float {0,1}, bits int32 words, stats int32[7])."""
+    _need_cuda(alpha_zyx, "alpha")
+    assert alpha_zyx.is_contiguous() and alpha_zyx.dtype == torch.float32
+    d, h, w = alpha_zyx.shape
+    dev = alpha_zyx.device
+    tmp = torch.empty_like(alpha_zyx)
+    vol = torch.empty_like(alpha_zyx)
+    bits = torch.empty(((d * h * w + 31) // 32,), device=dev, dtype=torch.int32)
+    stats = torch.empty((7,), device=dev, dtype=torch.int32)
+    with TIMER.span("alpha_mask_build"):
+        check(_lib.lib().jt_alpha_mask_build(_p(alpha_zyx), w, h, d, float(thres), _p(tmp), _p(vol), _p(bits),
+                                             _p(stats), _stream()), "jt_alpha_mask_build")
+    return vol, bits, stats
+
+
+def resize_bilinear_cl(x, h2, w2):
+    """[1,C,H,W] channel-last factor -> [1,C,h2,w2] channel-last (bilinear, align_corners=True)."""
+    _need_cuda(x, "factor")
+    xp = phys_cl(x)
+    h, w, c = xp.shape
+    out = torch.empty((h2, w2, c), device=x.device, dtype=torch.float32)
+    with TIMER.span("resize_bilinear"):
+        check(_lib.lib().jt_resize_bilinear_cl(_p(xp), h, w, c, _p(out), int(h2), int(w2), _stream()),
+              "jt_resize_bilinear_cl")
+    return out.unsqueeze(0).permute(0, 3, 1, 2)

@@ -51,7 +51,7 @@ class AlphaGridMask(torch.nn.Module):
     """Binary occupancy volume (reference tensorBase.py:80-98) + its bit-packed
     device copy used by the ray-march kernel."""
 
-    def __init__(self, device, aabb, alpha_volume):
+    def __init__(self, device, aabb, alpha_volume, packed_bits=None):
         super().__init__()
         self.device = device
         self.aabb = aabb.to(device)
@@ -60,10 +60,15 @@ class AlphaGridMask(torch.nn.Module):
         self.alpha_volume = alpha_volume.view(1, 1, *alpha_volume.shape[-3:]).to(device)
         d, h, w = self.alpha_volume.shape[-3:]
         self.gridSize = torch.LongTensor([w, h, d]).to(device)
-        self._pack()
+        self._pack(packed_bits)
 
-    def _pack(self):
+    def _pack(self, packed_bits=None):
         d, h, w = self.alpha_volume.shape[-3:]
+        if packed_bits is not None:          # already bit-packed by jt_alpha_mask_build
+            self.bits = packed_bits
+            self.h_dims = ints([w, h, d])
+            self.h_geom = floats(self.aabb[0].tolist() + self.invgridSize.tolist())
+            return
         flat = (self.alpha_volume.reshape(-1) > 0).to(torch.int64)
         pad = (-flat.numel()) % 32
         if pad:
@@ -150,6 +155,7 @@ class B200_VMSplit(torch.nn.Module):
         # supported, else the fp32 SIMT head; "fp32" forces the strict-parity path; "tc" insists.
         self.head_precision = "auto"
         self.tc_fwd_split = 2
+        self._reg_cache = None
         self.reset(aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
                    distance_scale, rayMarch_weight_thres, fea2denseAct, near_far, step_ratio, shadingMode, pos_pe,
                    view_pe, fea_pe, featureC, volume_init_scale, volume_init_bias)
@@ -269,17 +275,54 @@ class B200_VMSplit(torch.nn.Module):
             for p in plist:
                 p.requires_grad = flag
 
+    # ---------------------------------------------------------------- per-step regularisers (section 8f-2)
+    _REG_TERMS = (1, 1, 1, 0, 0, 0, 2, 2, 2, 0, 0, 0)      # TV slot: density planes -> 1, app planes -> 2
+    _REG_L1 = (1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0)         # L1 covers density planes and lines
+
+    def _reg_factors(self):
+        return [*self.density_plane, *self.density_line, *self.app_plane, *self.app_line]
+
+    def _reg_node(self):
+        """(L1, TV_density, TV_app) from ONE sweep over the factors, shared by the three methods the
+        reference calls back to back (model/tensorf.py:127-130); recomputed when a factor changes."""
+        fs = self._reg_factors()
+        key = tuple((id(p), p._version, p.requires_grad) for p in fs) + (torch.is_grad_enabled(),)
+        if self._reg_cache is None or self._reg_cache[0] != key:
+            from .sweeps import FieldRegularizers
+            self._reg_cache = (key, FieldRegularizers.apply(self._REG_TERMS, self._REG_L1, *fs))
+        return self._reg_cache[1]
+
     def density_L1(self):
-        total = 0
-        for i in range(3):
-            total = total + torch.mean(torch.abs(self.density_plane[i])) + torch.mean(torch.abs(self.density_line[i]))
-        return total
+        """tensoRF.py:212-216."""
+        return self._reg_node()[0]
 
     def TV_loss_density(self, reg):
-        return sum(reg(self.density_plane[i]) * 1e-2 for i in range(3))
+        """tensoRF.py:218-222 with reg = TVLoss (tensorBase.py:16-41); only its weight is read."""
+        return self._reg_node()[1] * float(getattr(reg, "TVLoss_weight", 1.0))
 
     def TV_loss_app(self, reg):
-        return sum(reg(self.app_plane[i]) * 1e-2 for i in range(3))
+        """tensoRF.py:224-228."""
+        return self._reg_node()[2] * float(getattr(reg, "TVLoss_weight", 1.0))
+
+    @torch.no_grad()
+    def regularize_(self, w_l1=0.0, w_tv_density=0.0, w_tv_app=0.0, values=True):
+        """Fused fast path: p.grad += d/dp (w_l1*L1 + w_tv_density*TV_density + w_tv_app*TV_app) for all factors in
+        one sweep, without autograd nodes; returns the [3] value tensor (or None). Terms with a zero weight are
+        not swept (Blender configs: TV weights are 0, bat_blender_VM.yaml:138-139)."""
+        from . import sweeps
+        fs = [p for p in self._reg_factors()]
+        xs = [ops.phys_cl(p.data) for p in fs]
+        out = sweeps.reg_values(xs, self._REG_TERMS, self._REG_L1) if values else None
+        sel = [i for i, p in enumerate(fs) if p.requires_grad]
+        gs = []
+        for i in sel:
+            if fs[i].grad is None:
+                fs[i].grad = torch.zeros_like(fs[i], memory_format=torch.preserve_format)
+            gs.append(ops.phys_cl(fs[i].grad))
+            assert gs[-1].data_ptr() == fs[i].grad.data_ptr(), "gradient buffers must be channel-last like the factors"
+        sweeps.reg_grads_([xs[i] for i in sel], gs, [self._REG_TERMS[i] for i in sel],
+                          [self._REG_L1[i] for i in sel], (w_l1, w_tv_density, w_tv_app))
+        return out
 
     # ---------------------------------------------------------------- geometry blobs for the C ABI
     def _h_geom(self):
@@ -419,18 +462,21 @@ class B200_VMSplit(torch.nn.Module):
         if mode != "bilinear":
             raise _lib.JtError(f"grid_sample_interp_mode={mode!r}: only 'bilinear' is implemented (all reference configs)")
 
+    def _density_factorset(self):
+        """Density factors as the last forward saw them (blurred with the cached density kernel, batBase.py:37)."""
+        planes, lines = self._blurred(self.density_plane, self.density_line,
+                                      self.kernel_density if self.c2f_mode is not None else None)
+        return ops.FactorSet([p.detach() for p in planes], [l.detach() for l in lines])
+
+    @torch.no_grad()
     def compute_alpha(self, xyz_locs, length=1):
-        """BatBase.compute_alpha (batBase.py:27-42); reuses the density kernel cached by the last forward."""
-        if self.alphaMask is not None:
-            alpha_mask = self.alphaMask.sample_alpha(xyz_locs) > 0
-        else:
-            alpha_mask = torch.ones_like(xyz_locs[:, 0], dtype=bool)
-        sigma = torch.zeros(xyz_locs.shape[:-1], device=xyz_locs.device)
-        xyz = self.normalize_coord(xyz_locs[alpha_mask])
-        if xyz.shape[0] > 0:
-            feat = self.compute_densityfeature(xyz, self.kernel_density, self.c2f_mode)
-            sigma[alpha_mask] = self.feature2density(feat)
-        return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
+        """BatBase.compute_alpha (batBase.py:27-42) as one kernel: mask test, normalisation, density gather,
+        activation, 1 - exp(-sigma * length). Reuses the density kernel cached by the last forward."""
+        shape = xyz_locs.shape[:-1]
+        a = ops.field_alpha(self._density_factorset(), self._h_geom(), self.density_shift,
+                            0 if self.fea2denseAct == "softplus" else 1, float(length), xyz=xyz_locs,
+                            mask=self.alphaMask)
+        return a.view(shape)
 
     # ---------------------------------------------------------------- forward (batBase.py:44-165)
     def forward(self, opt, center, ray_dir, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
@@ -444,6 +490,7 @@ class B200_VMSplit(torch.nn.Module):
         replaces the train-time background coin flip `torch.rand((1,)) < 0.5`."""
         self.opt = opt
         self._check_opt(opt)
+        self._reg_cache = None        # a new step: the regulariser node of the previous one is stale
         n_samples = N_samples if N_samples > 0 else self.nSamples
         dev = center.device
 
@@ -512,41 +559,54 @@ class B200_VMSplit(torch.nn.Module):
     # ---------------------------------------------------------------- maintenance (between steps)
     @torch.no_grad()
     def upsample_volume_grid(self, res_target):
-        """tensoRF.py:274-295: bilinear align_corners=True resize of every factor."""
+        """tensoRF.py:274-295: bilinear align_corners=True resize of every factor (jt_resize_bilinear_cl)."""
         res_target = [int(v) for v in res_target]
         for planes, lines in ((self.app_plane, self.app_line), (self.density_plane, self.density_line)):
             for i in range(3):
                 m0, m1 = MAT_MODE[i]
-                planes[i] = torch.nn.Parameter(_to_cl(F.interpolate(
-                    planes[i].data, size=(res_target[m1], res_target[m0]), mode="bilinear", align_corners=True)))
-                lines[i] = torch.nn.Parameter(_to_cl(F.interpolate(
-                    lines[i].data, size=(res_target[VEC_MODE[i]], 1), mode="bilinear", align_corners=True)))
+                planes[i] = torch.nn.Parameter(ops.resize_bilinear_cl(planes[i].data, res_target[m1], res_target[m0]))
+                lines[i] = torch.nn.Parameter(ops.resize_bilinear_cl(lines[i].data, res_target[VEC_MODE[i]], 1))
         self.update_stepSize(res_target)
+        self._reg_cache = None
+
+    def _dense_tables(self, gridSize):
+        return [torch.linspace(0, 1, int(g)).to(self.device) for g in gridSize]
+
+    @torch.no_grad()
+    def _dense_alpha_zyx(self, gridSize):
+        """alpha on the dense grid in [gz,gy,gx] order, one launch (tensorBase.py:618-633 without the xyz grid)."""
+        gridSize = [int(v) for v in gridSize]
+        return ops.field_alpha(self._density_factorset(), self._h_geom(), self.density_shift,
+                               0 if self.fea2denseAct == "softplus" else 1, float(self._h_step),
+                               lin=self._dense_tables(gridSize), grid=gridSize, mask=self.alphaMask)
 
     @torch.no_grad()
     def getDenseAlpha(self, gridSize=None):
-        """tensorBase.py:618-633."""
+        """tensorBase.py:618-633 -> (alpha [gx,gy,gz], dense_xyz [gx,gy,gz,3])."""
         gridSize = self._grid if gridSize is None else [int(v) for v in gridSize]
-        samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, gridSize[0]), torch.linspace(0, 1, gridSize[1]),
-                                             torch.linspace(0, 1, gridSize[2]), indexing="ij"), -1).to(self.device)
+        lin = self._dense_tables(gridSize)
+        samples = torch.stack(torch.meshgrid(*lin, indexing="ij"), -1)
         dense_xyz = self.aabb[0] * (1 - samples) + self.aabb[1] * samples
-        alpha = torch.zeros_like(dense_xyz[..., 0])
-        for i in range(gridSize[0]):
-            alpha[i] = self.compute_alpha(dense_xyz[i].view(-1, 3), self.stepSize).view((gridSize[1], gridSize[2]))
-        return alpha, dense_xyz
+        return self._dense_alpha_zyx(gridSize).permute(2, 1, 0), dense_xyz
 
     @torch.no_grad()
     def updateAlphaMask(self, gridSize=(200, 200, 200)):
-        """tensorBase.py:635-661: dense alpha -> max_pool3d(5) -> threshold -> new aabb."""
+        """tensorBase.py:635-661: dense alpha -> clamp -> max_pool3d(5) -> threshold -> mask + new aabb, four
+        launches and one 28-byte read-back (the reference synchronises here too: boolean indexing, prints)."""
         gridSize = [int(v) for v in gridSize]
-        alpha, dense_xyz = self.getDenseAlpha(gridSize)
-        dense_xyz = dense_xyz.transpose(0, 2).contiguous()
-        alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
-        alpha = F.max_pool3d(alpha, kernel_size=5, padding=2, stride=1).view(gridSize[::-1])
-        alpha = (alpha >= self.alphaMask_thres).to(alpha.dtype)
-        self.alphaMask = AlphaGridMask(self.device, self.aabb, alpha)
-        valid_xyz = dense_xyz[alpha > 0.5]
-        return torch.stack((valid_xyz.amin(0), valid_xyz.amax(0)))
+        alpha = self._dense_alpha_zyx(gridSize)
+        vol, bits, stats = ops.alpha_mask_build(alpha, self.alphaMask_thres)
+        st = stats.tolist()
+        if st[6] == 0:
+            raise RuntimeError("updateAlphaMask: no voxel reaches alphaMask_thres (the reference fails on the empty "
+                               "amin at tensorBase.py:654 as well)")
+        self.alphaMask = AlphaGridMask(self.device, self.aabb, vol, packed_bits=bits)
+        lin = self._dense_tables(gridSize)
+        lo = torch.stack([lin[a][st[2 * a]] for a in range(3)])
+        hi = torch.stack([lin[a][st[2 * a + 1]] for a in range(3)])
+        # dense_xyz = aabb[0]*(1-s) + aabb[1]*s is monotone per axis: amin/amax of the kept points sit at the
+        # extreme kept indices
+        return torch.stack((self.aabb[0] * (1 - lo) + self.aabb[1] * lo, self.aabb[0] * (1 - hi) + self.aabb[1] * hi))
 
     @torch.no_grad()
     def shrink(self, new_aabb):
@@ -570,6 +630,7 @@ class B200_VMSplit(torch.nn.Module):
             corrected[1] = (1 - hi) * self.aabb[0] + hi * self.aabb[1]
             new_aabb = corrected
         self.aabb = new_aabb
+        self._reg_cache = None
         new_size = b_r - t_l
         self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
 

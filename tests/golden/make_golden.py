@@ -69,6 +69,14 @@ def patched_rng(jitter):
         torch.rand_like, torch.rand = real_rl, real_r
 
 
+def ref_mat_mode():
+    return [[0, 1], [0, 2], [1, 2]]     # tensorBase.py:405
+
+
+def ref_vec_mode():
+    return [2, 1, 0]                    # tensorBase.py:406
+
+
 def build_reference(case, seed=0):
     tr, _ = ref_loader.load()
     ndc = case.get("ndc", False)

@@ -17,7 +17,7 @@ def module_from_golden(g, device="cuda:0"):
     missing, unexpected = m.load_state_dict(g["state_dict"], strict=False)
     assert not unexpected, unexpected
     assert not [k for k in missing if not k.startswith("alphaMask")], missing
-    if g["mask_volume"] is not None:
+    if g.get("mask_volume") is not None:
         m.alphaMask = jt.AlphaGridMask(device, g["aabb"].clone().to(device), g["mask_volume"].to(device))
     return m
 

@@ -86,9 +86,8 @@ def test_optimizer_groups_and_freeze():
     assert small(shading="SH").renderModule is None
 
 
-def test_upsample_and_param_state_roundtrip():
-    m = small(grid=(16, 16, 16))
-    m.upsample_volume_grid([24, 20, 28])
+def test_param_state_roundtrip():
+    m = small(grid=(24, 20, 28))
     assert m.density_plane[0].shape == (1, 8, 20, 24) and m.density_line[0].shape == (1, 8, 28, 1)
     assert m.app_plane[2].permute(0, 2, 3, 1).is_contiguous()
     assert m.gridSize.tolist() == [24, 20, 28]
@@ -101,12 +100,23 @@ def test_upsample_and_param_state_roundtrip():
     assert torch.equal(m2.app_plane[1], m.app_plane[1])
 
 
-def test_regularisers_run_on_channel_last_params():
+def test_sweeps_and_maintenance_have_no_cpu_fallback():
+    """Regularisers, optimiser step, upsampling and the alpha-mask update run as CUDA kernels only."""
+    from joint_tensorf_b200.sweeps import FusedAdam
     m = small()
-    l1 = m.density_L1()
-    l1.backward()
-    assert m.density_plane[0].grad is not None and m.app_plane[0].grad is None
-    assert float(l1) > 0
+    for call in (m.density_L1, lambda: m.TV_loss_density(None), lambda: m.regularize_(1e-4),
+                 lambda: m.upsample_volume_grid([20, 20, 20]), lambda: m.updateAlphaMask((8, 8, 8)),
+                 lambda: m.compute_alpha(torch.zeros(4, 3), 0.1)):
+        with pytest.raises(jt._lib.JtError):
+            call()
+    opt = FusedAdam(m.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99))
+    assert [g["lr"] for g in opt.param_groups] == [0.02] * 4 + [1e-3] * 2
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(jt._lib.JtError):
+        opt.step()
+    with pytest.raises(jt._lib.JtError):
+        FusedAdam(m.parameters(), weight_decay=0.1)
 
 
 def test_unsupported_options_fail_loudly():

@@ -52,3 +52,56 @@ def test_camera_oracle_matches_reference_golden(name):
     loss = (center * g["g_center"]).sum() + (ray * g["g_ray"]).sum()
     loss.backward()
     assert rel_err(se3.grad, g["d_se3"]) <= 1e-5
+
+
+def test_field_oracle_regularisers_and_adam_match_reference_golden():
+    """oracle/field_oracle.py against the live reference's density_L1 / TV_loss_* / torch.optim.Adam run
+    (tests/golden/make_golden_field.py)."""
+    from oracle import field_oracle as fo
+    g = load_golden("field_reg_adam")
+    params = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    l1, tvd, tva = fo.density_l1(params), fo.tv_loss_density(params), fo.tv_loss_app(params)
+    for got, ref in zip((l1, tvd, tva), g["values"]):
+        assert abs(float(got) - ref) <= 1e-6 * abs(ref)
+    w = g["weights"]
+    (w[0] * l1 + w[1] * tvd + w[2] * tva).backward()
+    for k, ref in g["reg_grads"].items():
+        assert rel_err(params[k].grad, ref) <= 1e-6, k
+    # three Adam steps with the reference's groups (factors lr_index, basis + head lr_basis) and lr decay
+    p = {k: v.clone() for k, v in g["state_dict"].items()}
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in p.items()}
+    lr = {k: (g["lr_index"] if k.split(".")[0] in ("density_plane", "density_line", "app_plane", "app_line")
+              else g["lr_basis"]) for k in g["param_names"]}
+    for it, grads in enumerate(g["step_grads"]):
+        for k in g["param_names"]:
+            fo.adam_step(p[k], grads[k], m[k], v2[k], it + 1, lr[k] * g["decay"] ** it)
+    for k in g["param_names"]:
+        assert rel_err(p[k], g["final"][k]) <= 1e-6, k
+        assert rel_err(m[k], g["adam_state"][k]["exp_avg"]) <= 1e-6, k
+        assert rel_err(v2[k], g["adam_state"][k]["exp_avg_sq"]) <= 1e-6, k
+
+
+def test_field_oracle_maintenance_matches_reference_golden():
+    """updateAlphaMask / shrink / upsample restatements against the live reference run."""
+    from oracle import field_oracle as fo
+    g = load_golden("field_maintenance")
+    grid = list(g["case"]["grid"])
+    pts = fo.dense_grid_points(g["aabb"], g["mask_grid"])
+    field = field_from_golden(dict(g, mask_volume=None), requires_grad=False)
+    fc = vo.grid_constants(field.aabb, field.grid, field.step_ratio)
+    with torch.no_grad():
+        alpha = vo.compute_alpha(field, pts.view(-1, 3), fc["step"]).view(g["mask_grid"])
+    assert (alpha - g["dense_alpha"]).abs().max() <= 1e-7
+    vol, new_aabb = fo.alpha_mask_from_dense(g["dense_alpha"], pts, g["alpha_thres"])
+    assert torch.equal(vol, g["mask_volume"])
+    assert torch.equal(new_aabb, g["new_aabb"])
+    t_l, b_r = fo.shrink_bounds(g["aabb"], fc["units"], grid, g["new_aabb"])
+    assert (b_r - t_l).tolist() == g["shrunk_grid"]
+    shr = fo.shrink_factors(g["state_dict"], t_l, b_r)
+    for k, ref in g["shrunk"].items():
+        assert torch.equal(shr[k], ref), k
+    assert torch.allclose(fo.shrink_corrected_aabb(g["aabb"], grid, t_l, b_r), g["shrunk_aabb"], atol=0, rtol=0)
+    up = fo.upsample_factors(g["shrunk"], g["up_target"])
+    for k, ref in g["upsampled"].items():
+        assert torch.equal(up[k], ref), k

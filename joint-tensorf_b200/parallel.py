@@ -63,6 +63,56 @@ class GradBucket:
         return work
 
 
+class OverlappedGradSync:
+    """Sum the gradients of a step across ranks while its backward is still running.
+
+    `B200_VMSplit.grad_sync = OverlappedGradSync()` makes the render node's backward hand over its flat gradient
+    bucket in two parts: the appearance-factor gradients (3/4 of the bytes, complete after the appearance scatter)
+    are all-reduced on NCCL's stream while the density scatter runs; the rest (density factors, basis_mat, head)
+    follows and the backward's stream waits for both before the node returns, so whatever consumes the gradients
+    next (p.grad, the adjoint blur -- linear, so reducing before it is the same sum) sees cross-rank sums.
+    `finish(extra)` reduces the few gradients produced by later autograd nodes (se3_refine). Sums only: scale the
+    loss by 1/world_size for a mean (no extra pass over the bucket). World size 1: every call is a no-op."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.works = []
+        self.bytes = 0
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce(self, t):
+        if self._active() and t.numel() > 0:
+            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.bytes += t.numel() * t.element_size()
+
+    def on_app_grads(self, region):
+        self._reduce(region)
+
+    def on_rest(self, region):
+        self._reduce(region)
+        self.wait()
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+    def finish(self, extra=()):
+        """extra: parameters whose .grad was produced outside the render node (e.g. se3_refine)."""
+        gs = [p.grad for p in extra if p.grad is not None]
+        if gs and self._active():
+            cat = torch.cat([g.reshape(-1) for g in gs])
+            self._reduce(cat)
+            self.wait()
+            o = 0
+            for g in gs:
+                g.copy_(cat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+        self.wait()
+
+
 def seed_all_ranks(seed):
     """Host RNG draws the reference makes per step (np.random.choice blur scale
     tensorf.py:198, torch.rand bg flip batBase.py:154, randperm ray_idx) must be

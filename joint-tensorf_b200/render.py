@@ -243,42 +243,54 @@ class VMRender(torch.autograd.Function):
                                     int(cfg.white_bg), shade_act, _p(dout), _p(dsig), _p(dnorm), _stream()),
                   "jt_render_bwd")
 
-        # one flat zero-filled bucket for all 12 factor gradients (one memset; also the
-        # unit the data-parallel all-reduce works on)
-        shapes = [p.shape for p in dfs.planes] + [l.shape for l in dfs.lines] + \
-                 [p.shape for p in afs.planes] + [l.shape for l in afs.lines]
+        # One flat zero-filled bucket for every gradient this node produces (one memset; also the unit the
+        # data-parallel all-reduce works on): [app planes, app lines | density planes, density lines | basis, head].
+        # The appearance part comes first and is complete first, so a gradient synchroniser
+        # (parallel.OverlappedGradSync) can reduce it across ranks while the density scatter still runs.
+        sync = getattr(cfg, "grad_sync", None)
+        shapes = [p.shape for p in afs.planes] + [l.shape for l in afs.lines] + \
+                 [p.shape for p in dfs.planes] + [l.shape for l in dfs.lines] + \
+                 [b["basis_w"].shape] + [t.shape for t in b["head"]]
         sizes = [int(torch.Size(s).numel()) for s in shapes]
         flat = torch.zeros((sum(sizes),), device=dev)
         views, o = [], 0
         for s, n in zip(shapes, sizes):
             views.append(flat[o:o + n].view(s))
             o += n
-        gdp, gdl, gap, gal = views[0:3], views[3:6], views[6:9], views[9:12]
+        gap, gal, gdp, gdl = views[0:3], views[3:6], views[6:9], views[9:12]
+        g_basis, head_grads = views[12], views[13:]
+        n_app = sum(sizes[0:6])
 
         d_o = torch.empty((N, 3), device=dev)
         d_d = torch.empty((N, 3), device=dev)
         with TIMER.span("ray_init"):
             check(lib.jt_ray_init(_p(b["rays_d"]), _p(dnorm), N, _p(d_o), _p(d_d), _stream()), "jt_ray_init")
-        ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
-                            cfg.h_inv, d_o, d_d)
 
-        g_basis = torch.zeros_like(b["basis_w"])
         # tensor-core head: dcomps crosses HBM as bf16 (its GEMM operands are bf16 already)
         dcomps = torch.empty((cap, afs.ctot), device=dev, dtype=torch.bfloat16 if cfg.head == "tc" else torch.float32)
         if cfg.head == "tc":
             w1, b1, w2, b2, w3, b3 = b["head"]
-            head_grads = [torch.zeros_like(t) for t in b["head"]]
             ops.head_bwd_tc(dout, b["feat"], b["basis_w"], w1, w2, w3, b["a_count"], cap, cfg.fea_prog, dcomps,
                             ws["stage"], (g_basis, *head_grads))
         else:
-            dfeat, head_grads = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
-                                               b["a_count"], cap, b["head"], dev)
+            dfeat, hg = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
+                                       b["a_count"], cap, b["head"], dev)
+            for dst, src in zip(head_grads, hg):
+                dst.copy_(src)
             ops.gemm_tn(dfeat, ldf, b["comps"], afs.ctot, b["a_count"], cap, F, afs.ctot, g_basis, afs.ctot, None,
                         name="basis_bwd_w")
             ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
                         afs.ctot, F, 0, name="basis_bwd_x")
         ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
                             cfg.n_samples, cfg.h_inv, d_o, d_d)
+        if sync is not None:
+            sync.on_app_grads(flat[:n_app])          # 3/4 of the bytes: reduced while the density scatter runs
+        ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+                            cfg.h_inv, d_o, d_d)
+        if sync is not None:
+            # the current stream waits here for both reductions: whatever autograd does with the views next (hand
+            # them to p.grad, clone them, feed the adjoint blur) sees the cross-rank sums
+            sync.on_rest(flat[n_app:])
 
         gdpn, gdln = FactorSet.grads_as_nchw(gdp, gdl)
         gapn, galn = FactorSet.grads_as_nchw(gap, gal)

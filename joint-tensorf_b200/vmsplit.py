@@ -156,6 +156,7 @@ class B200_VMSplit(torch.nn.Module):
         self.head_precision = "auto"
         self.tc_fwd_split = 2
         self._reg_cache = None
+        self.grad_sync = None      # parallel.OverlappedGradSync when training data-parallel
         self.reset(aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
                    distance_scale, rayMarch_weight_thres, fea2denseAct, near_far, step_ratio, shadingMode, pos_pe,
                    view_pe, fea_pe, featureC, volume_init_scale, volume_init_bias)
@@ -535,6 +536,7 @@ class B200_VMSplit(torch.nn.Module):
                                            sum(self.app_n_comp) == 144):
             cfg.head = "tc"
 
+        cfg.grad_sync = self.grad_sync
         dp, dl, ap, al = self._blurred_all(self.kernel_density, self.kernel_color)
         head = self.renderModule.head_params() if self.renderModule is not None else []
         return VMRender.apply(cfg, center.reshape(-1, 3), ray_dir.reshape(-1, 3), aux, *dp, *dl, *ap, *al,

@@ -45,6 +45,43 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+def _worker_overlap(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sync = parallel.OverlappedGradSync()
+    flat = torch.arange(20, dtype=torch.float32) * (rank + 1)          # the render node's flat gradient bucket
+    sync.on_app_grads(flat[:12])                                        # appearance part first (async)
+    sync.on_rest(flat[12:])                                             # the rest, then wait for both
+    se3 = torch.nn.Parameter(torch.zeros(4, 6))
+    se3.grad = torch.full((4, 6), float(rank + 1))
+    frozen = torch.nn.Parameter(torch.zeros(3))                         # no gradient: skipped
+    sync.finish([se3, frozen])
+    tot = sum(r + 1 for r in range(world))
+    ok = torch.equal(flat, torch.arange(20, dtype=torch.float32) * tot) and \
+        torch.equal(se3.grad, torch.full((4, 6), float(tot))) and not sync.works
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_sync_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_overlap, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_overlapped_grad_sync_is_a_noop_without_a_process_group():
+    sync = parallel.OverlappedGradSync()
+    flat = torch.ones(8)
+    sync.on_app_grads(flat[:4])
+    sync.on_rest(flat[4:])
+    sync.finish([])
+    assert torch.equal(flat, torch.ones(8)) and sync.bytes == 0
+
+
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 4096, 4097):
         for world in (1, 2, 3, 8):

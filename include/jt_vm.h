@@ -291,6 +291,40 @@ int jt_alpha_mask_build(const float* alpha, int W, int H, int D, float thres, fl
  * channel-last layout: in [H][W][C] -> out [H2][W2][C]; a line factor is W = W2 = 1. */
 int jt_resize_bilinear_cl(const float* in, int H, int W, int C, float* out, int H2, int W2, cudaStream_t stream);
 
+/* ---- 2-D supervision pre-processing and the render loss (next row) -- */
+/* Model.process_GT_images (model/nerf.py:57-113): separable blur of n_img single-channel images [n_img][H][W]
+ * (the reference reshapes [B,3,H,W] to [B*3,H,W]): replicate pad + cross-correlation with h_taps (HOST, ntaps odd,
+ * <= 257; 201 in the shipped YAMLs) along W (nerf.py:102-103), then the same along H (105-106). tmp: n_img*H*W floats.
+ * `in` may not alias `out` or `tmp`. Taps come from kernels.get_gaussian_kernel / get_average_kernel (kernels.py:16-41). */
+int jt_image_blur(const float* in, float* out, float* tmp, int n_img, int H, int W, const float* h_taps, int ntaps,
+                  cudaStream_t stream);
+/* Model.get_edge_mask (model/nerf.py:116-149) on images [n_img][3][H][W]: replicate pad, the two 3x3 Sobel
+ * correlations summed over the colour channels, gg = sqrt(Gx^2 + Gy^2) [n_img][H*W]; then
+ *   soft != 0: mask_f = gg / max_b(gg)            (nerf.py:140-143)
+ *   soft == 0: mask_u8 = gg > mean_b(gg) * thresh (nerf.py:144-148; hard_edge_mask_mean_thresh, default 1.25).
+ * ws: jt_edge_mask_ws_floats(n_img, H, W) floats of scratch; stats: [n_img][2] = {max, mean} per image.
+ * The per-image reductions use a fixed order (deterministic). */
+long long jt_edge_mask_ws_floats(int n_img, int H, int W);
+int jt_edge_mask(const float* images, int n_img, int H, int W, int soft, float thresh, float* gg, float* ws,
+                 float* stats, float* mask_f, uint8_t* mask_u8, cudaStream_t stream);
+/* The render term of Graph.compute_loss (model/tensorf.py:99-124) with the pixel gathers of :101-102,113 fused:
+ * rgb [n_views][n_rays][3]; images [n_cache][3][hw] (the blurred GT cache); mask [n_cache][hw], float
+ * (mask_kind 1) or uint8 (mask_kind 2), or NULL (mask_kind 0); ray_idx [n_rays] pixel indices shared by all views
+ * (NULL: n_rays == hw, identity); view_idx [n_views] rows of the cache (NULL: identity).
+ *   mode 0: MSE(rgb, image)                                                    (tensorf.py:124)
+ *   mode 1: MSE(rgb*w, image*w), w = m*edge_factor + non_edge_factor            (soft_edge_loss, :114-116)
+ *   mode 2: edge_factor*MSE(rgb*m, image*m) + non_edge_factor*MSE(rgb*(1-m), image*(1-m))   (:118-122)
+ * MSE = nanmean of the squared difference (base.py:259-261). ws4: 4 doubles {S_a, S_b, count_a, count_b} kept for
+ * the backward; loss: 1 float. One CTA, fixed summation order. */
+int jt_render_loss_fwd(const float* rgb, const float* images, const void* mask, int mask_kind, const int* ray_idx,
+                       const int* view_idx, int n_views, int n_rays, int hw, int mode, float edge_factor,
+                       float non_edge_factor, double* ws4, float* loss, cudaStream_t stream);
+/* d loss / d rgb [n_views][n_rays][3], multiplied by the upstream gradient g_loss[0] (device scalar; NULL = 1). */
+int jt_render_loss_bwd(const float* rgb, const float* images, const void* mask, int mask_kind, const int* ray_idx,
+                       const int* view_idx, int n_views, int n_rays, int hw, int mode, float edge_factor,
+                       float non_edge_factor, const double* ws4, const float* g_loss, float* d_rgb,
+                       cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 def golden_names():
     """Render-path fixtures (tests/golden/make_golden.py)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-    return [n for n in names if not n.startswith(("camera_", "field_"))]
+    return [n for n in names if not n.startswith(("camera_", "field_", "image_"))]
 
 
 def camera_golden_names():

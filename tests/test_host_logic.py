@@ -162,3 +162,27 @@ def test_synthetic_rays_are_deterministic_and_hit_the_box():
     assert 0.3 < float(valid.float().mean()) < 0.9
     o, d, _ = jt.synth.llff_ndc_rays(128, 4)
     assert torch.allclose(o[:, 2], torch.full((128,), -1.0), atol=1e-5)
+
+
+def test_supervision_blur_taps_and_scales_match_oracle():
+    """supervision.blur_taps_2d / _scales (host side of process_GT_images, nerf.py:63-83) against the oracle's
+    restatement for both golden option sets, every scale, several iterations."""
+    import torch
+    from common import load_golden
+    from joint_tensorf_b200 import supervision as sv
+    from joint_tensorf_b200.options import Namespace
+    from oracle import image_oracle as io
+    g = load_golden("image_prep")
+    h, w = g["images"].shape[-2:]
+    for name, o in g["opts"].items():
+        opt = Namespace(dict({k: v for k, v in o.items() if k != "it"}, H=h, W=w))
+        assert sv._scales(opt) == io.scales(o)
+        for it in (0, o["it"], 333, 999):
+            for sc in io.scales(o):
+                taps, width = sv.blur_taps_2d(opt, it, sc)
+                bp = torch.tensor(io.interp_schedule(float(it / o["max_iter"]), o["blur_2d_c2f_schedule"])) * sc
+                wref = bp * (w + h) / 2
+                assert abs(width - float(wref)) <= 1e-12
+                kref = (io.gaussian_kernel if o["blur_2d_mode"] == "uniform-gaussian" else io.average_kernel)(
+                    wref, o["blur_2d_c2f_kernel_size"])
+                assert taps.shape == kref.shape and (taps - kref).abs().max() <= 1e-7, (name, it, sc)

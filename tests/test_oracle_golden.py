@@ -105,3 +105,47 @@ def test_field_oracle_maintenance_matches_reference_golden():
     up = fo.upsample_factors(g["shrunk"], g["up_target"])
     for k, ref in g["upsampled"].items():
         assert torch.equal(up[k], ref), k
+
+
+def _image_loss_kind(l):
+    """The branch of model/tensorf.py:104-124 a golden loss case takes."""
+    f = l["flags"]
+    on = f.get("edge_mask_on_render_loss", False) and (l["it"] % 2 == 0 if f.get("alternate_edge_loss", False) else True)
+    if not (on and l["it"] < f["edge_mask_before_iter"]):
+        return 0
+    return 1 if f.get("soft_edge_loss", False) else 2
+
+
+def test_image_oracle_matches_reference_golden():
+    """oracle/image_oracle.py against the live reference's process_GT_images / get_edge_mask / compute_loss
+    (tests/golden/make_golden_image.py). Same ATen operators in the same order -> exact or 1e-7."""
+    from oracle import image_oracle as io
+    g = load_golden("image_prep")
+    images = g["images"]
+    masks = {}
+    for name, o in g["opts"].items():
+        ref = g["prep"][name]
+        blurred = io.process_gt_images(o, images, o["it"])
+        assert sorted(blurred) == sorted(ref["blurred"])
+        for sc, img in blurred.items():
+            assert (img - ref["blurred"][sc]).abs().max() <= 1e-6, (name, sc)
+            m = io.edge_mask(img, o.get("soft_edge_mask", False), o.get("hard_edge_mask_mean_thresh", 1.25))
+            assert m.dtype == ref["edge"][sc].dtype
+            if m.dtype == torch.uint8:
+                assert torch.equal(m, ref["edge"][sc]), (name, sc)
+            else:
+                assert (m - ref["edge"][sc]).abs().max() <= 1e-6, (name, sc)
+        assert blurred[0.0] is images                       # width < 0.01: the raw images (nerf.py:95-97)
+        masks[name] = ref["edge"][1.0]
+    for l in g["losses"]:
+        rgb = g["rgb"].clone()
+        if l["nan"]:
+            rgb[1, 7, 2] = float("nan")
+        rgb.requires_grad_(True)
+        kind = _image_loss_kind(l)
+        val = io.render_loss(rgb, images, g["ray_idx"], masks.get(l["mask"]), kind, 1.5, 0.5)
+        assert abs(float(val) - float(l["loss"])) <= 1e-7, l["tag"]
+        (d,) = torch.autograd.grad(val * l["upstream"], rgb)
+        assert torch.allclose(d, l["d_rgb"], rtol=1e-6, atol=1e-9, equal_nan=True), l["tag"]
+    v = g["loss_val"]
+    assert abs(float(io.render_loss(v["rgb"], images, None, None, 0, 1.5, 0.5)) - float(v["loss"])) <= 1e-7

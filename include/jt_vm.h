@@ -178,6 +178,20 @@ int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, const float* W
                    const float* W3, const int* n_dev, int n_max, float fea_progress, void* dcomps, int dcomps_bf16, void* stage,
                    float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                    cudaStream_t stream);
+/* SH shading on the tensor-core path (SHRender tensorBase.py:68-72 with eval_sh_bases(2, .)
+ * sh.py:88-113; BASELINE config "app_dim 27 SH shading").
+ * jt_app_basis_sh_fwd_tc = jt_app_basis_fwd_tc whose epilogue shades the sample straight out of
+ * TMEM: rgb [A][4] = relu(sum_k Y_k(dir) feat[c*9+k] + 0.5); the 27 features never reach HBM,
+ * featdir [A][32] only receives the view direction (floats 28..30) for the backward.
+ * jt_sh_bwd_tc = backward of basis_mat + SHRender: dout [A][4] (gradient at the pre-activation,
+ * jt_render_bwd with shade_act 2) -> DF = dout (x) Y (bf16) -> dcomps [A][144] = DF * Wb on
+ * tcgen05; ADDS d basis_mat into gWb [27][144] from the component tiles the forward staged. */
+int jt_app_basis_sh_fwd_tc(int split, const void* const* h_factors, const int* h_dims, const float* samp,
+                           const int* aidx, const int* sidx, const float* rays_d, int n_samples, int normalize_dir,
+                           const float* Wb, const int* n_dev, int n_max, float* featdir, float* rgb, void* stage,
+                           cudaStream_t stream);
+int jt_sh_bwd_tc(const float* dout, const float* featdir, int ldf, const float* Wb, const int* n_dev, int n_max,
+                 void* dcomps, int dcomps_bf16, void* stage, float* gWb, cudaStream_t stream);
 
 /* ---- K4: alpha compositing --------------------------------------------- */
 /* feature2density (tensorBase.py:696-700; act 0 softplus, 1 relu) + raw2alpha

@@ -33,17 +33,22 @@ struct GSmem {
 
 __device__ __forceinline__ uint2 pack4_bf16(float4 v) { return make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w)); }
 
-template <int SPLIT, bool SAVE>
+// SH = true: the epilogue also shades the sample with SHRender (tensorBase.py:68-72,
+// eval_sh_bases(2, .) sh.py:88-113): rgb = relu(sum_k Y_k(dir) feat[c*9+k] + 0.5); only the
+// view direction (for the backward) and rgb leave the kernel, the 27 features never do.
+template <int SPLIT, bool SAVE, bool SH>
 __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const float4* __restrict__ samp,
                                                               const int* __restrict__ aidx, const int* __restrict__ sidx,
                                                               const float* __restrict__ rays_d, int S, int normalize_dir,
                                                               const float* __restrict__ Wb, const int* __restrict__ n_dev,
                                                               int n_fixed, float* __restrict__ featdir,
+                                                              float* __restrict__ rgb_sh,
                                                               unsigned char* __restrict__ stage) {
     using L = GSmem<SPLIT>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ float sdir[SH ? TM : 1][3];       // view directions of the tile's rows (SH epilogue)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, grp = lane >> 2;
     const int n = n_dev ? *n_dev : n_fixed;
     unsigned char* wb_hi = smem + L::off_wb;
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
                 d0 /= nn; d1 /= nn; d2 /= nn;
             }
             __stcs(reinterpret_cast<float4*>(featdir + (size_t)row * FD + 28), make_float4(d0, d1, d2, 0.f));
+            if (SH) { sdir[r][0] = d0; sdir[r][1] = d1; sdir[r][2] = d2; }
         }
         fence_async_smem();
         tc_fence_before();
@@ -139,10 +145,24 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), f);
             const int erow = tile * TM + tid;
             if (erow < n) {
-                float4* dst = reinterpret_cast<float4*>(featdir + (size_t)erow * FD);
+                if (SH) {
+                    const float d[3] = {sdir[tid][0], sdir[tid][1], sdir[tid][2]};
+                    float y[9], c3[3];
+                    sh9(d, y);
 #pragma unroll
-                for (int q = 0; q < 7; ++q)
-                    __stcs(dst + q, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], q == 6 ? 0.f : f[4 * q + 3]));
+                    for (int c = 0; c < 3; ++c) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) s += y[k] * f[c * 9 + k];
+                        c3[c] = fmaxf(s + 0.5f, 0.f);
+                    }
+                    __stcs(reinterpret_cast<float4*>(rgb_sh) + erow, make_float4(c3[0], c3[1], c3[2], 0.f));
+                } else {
+                    float4* dst = reinterpret_cast<float4*>(featdir + (size_t)erow * FD);
+#pragma unroll
+                    for (int q = 0; q < 7; ++q)
+                        __stcs(dst + q, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], q == 6 ? 0.f : f[4 * q + 3]));
+                }
             }
         }
         if (SAVE && tid == 0) bulk_wait_read0();     // the tile may be overwritten by the next gather
@@ -159,12 +179,13 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
 
 using namespace jt;
 
-extern "C" int jt_app_basis_fwd_tc(int split, const void* const* h_factors, const int* h_dims, const float* samp,
-                                   const int* aidx, const int* sidx, const float* rays_d, int n_samples,
-                                   int normalize_dir, const float* Wb, const int* n_dev, int n_max, float* featdir,
-                                   void* stage, cudaStream_t stream) {
+static int app_basis_launch(int split, int sh, const void* const* h_factors, const int* h_dims, const float* samp,
+                            const int* aidx, const int* sidx, const float* rays_d, int n_samples, int normalize_dir,
+                            const float* Wb, const int* n_dev, int n_max, float* featdir, float* rgb, void* stage,
+                            cudaStream_t stream) {
     JT_CHECK_ARG(h_factors && h_dims && samp && aidx && sidx && rays_d && Wb && featdir && n_samples > 0);
     JT_CHECK_ARG(split == 1 || split == 2);
+    JT_CHECK_ARG(!sh || rgb);
     JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
     if (n_max <= 0) return JT_OK;
     Factors F;
@@ -174,18 +195,37 @@ extern "C" int jt_app_basis_fwd_tc(int split, const void* const* h_factors, cons
     int grid = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
     unsigned char* st = static_cast<unsigned char*>(stage);
     g_launches += 1;
-#define JT_LAUNCH_G(SP, SV)                                                                                          \
+#define JT_LAUNCH_G(SP, SV, SHV)                                                                                     \
     {                                                                                                                \
         const int smem = GSmem<SP>::total;                                                                           \
-        if (int rc = set_smem(app_basis_fwd_kernel<SP, SV>, smem)) return rc;                                        \
-        app_basis_fwd_kernel<SP, SV><<<grid, GT, smem, stream>>>(F, reinterpret_cast<const float4*>(samp), aidx,     \
-                                                                 sidx, rays_d, n_samples, normalize_dir, Wb, n_dev,  \
-                                                                 n_max, featdir, st);                                \
+        if (int rc = set_smem(app_basis_fwd_kernel<SP, SV, SHV>, smem)) return rc;                                   \
+        app_basis_fwd_kernel<SP, SV, SHV><<<grid, GT, smem, stream>>>(F, reinterpret_cast<const float4*>(samp),      \
+                                                                      aidx, sidx, rays_d, n_samples, normalize_dir,  \
+                                                                      Wb, n_dev, n_max, featdir, rgb, st);           \
     }
-    if (split == 1 && !st) JT_LAUNCH_G(1, false)
-    else if (split == 1) JT_LAUNCH_G(1, true)
-    else if (!st) JT_LAUNCH_G(2, false)
-    else JT_LAUNCH_G(2, true)
+#define JT_LAUNCH_GS(SP, SV) { if (sh) JT_LAUNCH_G(SP, SV, true) else JT_LAUNCH_G(SP, SV, false) }
+    if (split == 1 && !st) JT_LAUNCH_GS(1, false)
+    else if (split == 1) JT_LAUNCH_GS(1, true)
+    else if (!st) JT_LAUNCH_GS(2, false)
+    else JT_LAUNCH_GS(2, true)
+#undef JT_LAUNCH_GS
 #undef JT_LAUNCH_G
     JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_app_basis_fwd_tc(int split, const void* const* h_factors, const int* h_dims, const float* samp,
+                                   const int* aidx, const int* sidx, const float* rays_d, int n_samples,
+                                   int normalize_dir, const float* Wb, const int* n_dev, int n_max, float* featdir,
+                                   void* stage, cudaStream_t stream) {
+    return app_basis_launch(split, 0, h_factors, h_dims, samp, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, n_dev,
+                            n_max, featdir, nullptr, stage, stream);
+}
+
+extern "C" int jt_app_basis_sh_fwd_tc(int split, const void* const* h_factors, const int* h_dims, const float* samp,
+                                      const int* aidx, const int* sidx, const float* rays_d, int n_samples,
+                                      int normalize_dir, const float* Wb, const int* n_dev, int n_max, float* featdir,
+                                      float* rgb, void* stage, cudaStream_t stream) {
+    JT_CHECK_ARG(rgb);
+    return app_basis_launch(split, 1, h_factors, h_dims, samp, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, n_dev,
+                            n_max, featdir, rgb, stage, stream);
 }

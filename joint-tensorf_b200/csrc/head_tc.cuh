@@ -145,6 +145,49 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 constexpr int FD = 32;    // floats per feat/dir row written by app_basis_fwd_kernel: feat 0..26 | 27 pad | dir 28..30 | 31 pad
 
+// One row of the dcomps tile [128 x 144] (TMEM columns t_dc ..) -> global, fp32 or bf16 (DC16).
+// Two threads per row: hh = 0 writes columns [0,64) + [128,144), hh = 1 columns [64,128).
+// `t_dc` already carries the thread's TMEM lane offset.
+template <bool DC16>
+__device__ __forceinline__ void store_dcomps_row(uint32_t t_dc, int hh, bool live, int row, void* __restrict__ dcomps_out) {
+    float* dstf = reinterpret_cast<float*>(dcomps_out) + (size_t)(live ? row : 0) * CT;
+    uint4* dsth = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dcomps_out) + (size_t)(live ? row : 0) * CT);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float g[32];
+        const int c0 = 64 * hh + 32 * k;
+        tmem_ld32(t_dc + c0, g);
+        if (live) {
+            if (DC16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    __stcs(dsth + c0 / 8 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                                         pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    __stcs(reinterpret_cast<float4*>(dstf) + c0 / 4 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+            }
+        }
+    }
+    if (hh == 0) {
+        float g[16];
+        tmem_ld16(t_dc + 128, g);
+        if (live) {
+            if (DC16) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    __stcs(dsth + 16 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                                     pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    __stcs(reinterpret_cast<float4*>(dstf) + 32 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
+            }
+        }
+    }
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
     if (bytes > 48 * 1024)

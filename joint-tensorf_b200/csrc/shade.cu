@@ -279,20 +279,6 @@ __global__ void __launch_bounds__(256) pe_bwd_kernel(PEParams P, const float* __
 }
 
 // ------------------------------------------------------------------ SH (deg 2) shading
-__device__ __forceinline__ void sh9(const float d[3], float y[9]) {
-    const float x = d[0], yy_ = d[1], z = d[2];
-    y[0] = 0.28209479177387814f;
-    y[1] = -0.4886025119029199f * yy_;
-    y[2] = 0.4886025119029199f * z;
-    y[3] = -0.4886025119029199f * x;
-    const float xx = x * x, yy = yy_ * yy_, zz = z * z;
-    y[4] = 1.0925484305920792f * (x * yy_);
-    y[5] = -1.0925484305920792f * (yy_ * z);
-    y[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
-    y[7] = -1.0925484305920792f * (x * z);
-    y[8] = 0.5462742152960396f * (xx - yy);
-}
-
 // fwd: rgb[a][c] = relu(sum_k Y_k f[a][c*9+k] + 0.5); bwd: dfeat[a][c*9+k] = dout[a][c] * Y_k
 __global__ void __launch_bounds__(256) sh_kernel(int bwd, const float* __restrict__ feat, int ldf,
                                                  const int* __restrict__ aidx, const int* __restrict__ sidx,

@@ -216,45 +216,8 @@ __global__ void __launch_bounds__(NTB, 2) head_bwd_data_kernel(
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        // ---- S3: dcomps row -> global (fp32, or bf16 when DC16); hh = 0: columns [0,64) + [128,144), hh = 1: [64,128)
-        {
-            float* dstf = reinterpret_cast<float*>(dcomps_out) + (size_t)(live ? row : 0) * CT;
-            uint4* dsth = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dcomps_out) + (size_t)(live ? row : 0) * CT);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                float g[32];
-                const int c0 = 64 * hh + 32 * k;
-                tmem_ld32(lane_addr + T_DC + c0, g);
-                if (live) {
-                    if (DC16) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            __stcs(dsth + c0 / 8 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
-                                                                 pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            __stcs(reinterpret_cast<float4*>(dstf) + c0 / 4 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
-                    }
-                }
-            }
-            if (hh == 0) {
-                float g[16];
-                tmem_ld16(lane_addr + T_DC + 128, g);
-                if (live) {
-                    if (DC16) {
-#pragma unroll
-                        for (int q = 0; q < 2; ++q)
-                            __stcs(dsth + 16 + q, make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
-                                                             pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7])));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            __stcs(reinterpret_cast<float4*>(dstf) + 32 + q, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]));
-                    }
-                }
-            }
-        }
+        // ---- S3: dcomps row -> global (fp32, or bf16 when DC16)
+        store_dcomps_row<DC16>(lane_addr + T_DC, hh, live, row, dcomps_out);
         if (tid == 0) bulk_wait_read0();       // D2 / D1 / DF / DO have left shared memory
         tc_fence_before();
         __syncthreads();
@@ -280,6 +243,9 @@ __device__ __forceinline__ WGroup wgroup(int g) {
     }
 }
 
+// Groups [G0, G0 + NG) of wgroup() are accumulated: <0, 4> is the MLP_Fea head + basis_mat,
+// <3, 1> basis_mat alone (SH shading: jt_sh_bwd_tc).
+template <int G0, int NG>
 __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char* __restrict__ stage,
                                                             const int* __restrict__ n_dev, int n_fixed,
                                                             float* __restrict__ gWb, float* __restrict__ gW1,
@@ -304,14 +270,14 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const int items = my_tiles * 4;
+    const int items = my_tiles * NG;
 
     if (warp == 0 && lane == 0) {                 // ---- TMA producer
         for (int i = 0; i < items; ++i) {
             const int s = i % WG_STAGES, round = i / WG_STAGES;
             mbar_wait(&empty[s], (round & 1) ^ 1);
-            const int tile = blockIdx.x + (i >> 2) * gridDim.x;
-            const WGroup g = wgroup(i & 3);
+            const int tile = blockIdx.x + (i / NG) * gridDim.x;
+            const WGroup g = wgroup(G0 + i % NG);
             const unsigned char* src = stage + (size_t)tile * STAGE_TILE_BYTES;
             unsigned char* dst = smem + s * WG_STAGE_BYTES;
             mbar_expect_tx(&full[s], (uint32_t)(g.a_bytes + g.b_bytes));
@@ -323,13 +289,13 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
             const int s = i % WG_STAGES, round = i / WG_STAGES;
             mbar_wait(&full[s], round & 1);
             tc_fence_after();
-            const WGroup g = wgroup(i & 3);
+            const WGroup g = wgroup(G0 + i % NG);
             const uint32_t a = smem_u32(smem + s * WG_STAGE_BYTES), b = a + WG_A_REGION;
             const uint32_t idesc = idesc_bf16(128, g.n, 1, 1);
 #pragma unroll
             for (int ks = 0; ks < TM / 16; ++ks)       // K = 128 sample rows, 16 per MMA = 256 B
                 mma_bf16(tmem + g.col, smem_desc(a + ks * 256, 128, TM * 16), smem_desc(b + ks * 256, 128, TM * 16), idesc,
-                         (i >= 4 || ks > 0) ? 1u : 0u);
+                         (i >= NG || ks > 0) ? 1u : 0u);
             mma_commit(&empty[s]);
         }
         mma_commit(&done);
@@ -341,7 +307,7 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
         if (warp < 2) {                               // real rows are all < 64
             const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
             const int m = tid;
-            for (int c0 = 0; c0 < K1; c0 += 32) {     // dW1 / db1
+            for (int c0 = 0; G0 == 0 && c0 < K1; c0 += 32) {     // dW1 / db1
                 float v[32];
                 tmem_ld32(lane_addr + 0 + c0, v);
 #pragma unroll
@@ -351,7 +317,7 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
                     else if (r == -2) atomicAdd(gb1 + m, v[i]);
                 }
             }
-            for (int c0 = 0; c0 < K2; c0 += 16) {     // dW2 / db2, dW3 / db3
+            for (int c0 = 0; G0 == 0 && c0 < K2; c0 += 16) {     // dW2 / db2, dW3 / db3
                 float v[16], w[16];
                 tmem_ld16(lane_addr + 160 + c0, v);
                 tmem_ld16(lane_addr + 240 + c0, w);
@@ -377,6 +343,104 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------ SH shading (SHRender, tensorBase.py:68-72)
+// Backward of basis_mat + SHRender on the tensor cores. rgb = relu(sum_k Y_k(dir) feat[c*9+k] + 0.5),
+// so dfeat[c*9+k] = dpre[c] * Y_k(dir) needs only the view direction (kept by the forward in the
+// feat/dir rows) and dpre = dL/d(pre-activation) (jt_render_bwd folds relu' into it):
+//     DF[128x32] (bf16) = dpre (x) Y     ->  MMA  dcomps[128x144] = DF * Wb   (TMEM)  -> bf16 rows
+// DF is pushed to the staging area next to the forward's component tile A0, and the
+// basis_mat weight gradient is group 3 of the shared TMA -> tcgen05 wgrad pipeline.
+struct ShBwdSmem {
+    static constexpr int WBT = tile_bytes(CT, NB);
+    static constexpr int off_wbt = 0, off_df = off_wbt + WBT;
+    static constexpr int used = off_df + SZ_DF;
+    // two CTAs per SM at most: each allocates 256 of the SM's 512 TMEM columns
+    static constexpr int total = used > 100 * 1024 ? used : 100 * 1024;
+};
+
+template <bool DC16>
+__global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ featdir,
+                                                             int ldf, const float* __restrict__ Wb,
+                                                             const int* __restrict__ n_dev, int n_fixed,
+                                                             void* __restrict__ dcomps_out,
+                                                             unsigned char* __restrict__ stage) {
+    using L = ShBwdSmem;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TM - 1), hh = tid >> 7;
+    const int n = n_dev ? *n_dev : n_fixed;
+    unsigned char* wbt = smem + L::off_wbt;
+    unsigned char* DF = smem + L::off_df;
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    stage_tile(wbt, nullptr, CT, NB, [&](int ic, int m) { return m < F_ ? Wb[(size_t)m * CT + ic] : 0.f; });
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t phase = 0;
+
+    float4 g4, d4;                     // dpre and view direction of the NEXT tile's row (prefetched)
+    auto prefetch = [&](long long t) {
+        const long long rw = t * TM + r;
+        g4 = d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rw < n) {
+            g4 = __ldcs(reinterpret_cast<const float4*>(dout) + rw);
+            d4 = __ldcs(reinterpret_cast<const float4*>(featdir + (size_t)rw * ldf + 28));
+        }
+    };
+    prefetch(blockIdx.x);
+
+    for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
+        const int row = tile * TM + r;
+        const bool live = row < n;
+        unsigned char* st = stage + (size_t)tile * STAGE_TILE_BYTES;
+        // ---- DF row: columns c*9+k = dpre[c] * Y_k, 27..31 = 0; this thread: columns [16 hh, 16 hh + 16)
+        {
+            const float d[3] = {d4.x, d4.y, d4.z};
+            const float go[3] = {g4.x, g4.y, g4.z};
+            float y[9], df[16];
+            sh9(d, y);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int col = 16 * hh + e;             // hh is warp-uniform: both candidates are compile-time
+                const int c0 = e / 9, k0 = e % 9, c1 = (16 + e) / 9, k1 = (16 + e) % 9;
+                const float v0 = go[c0] * y[k0];
+                const float v1 = (16 + e) < F_ ? go[c1 < 3 ? c1 : 0] * y[k1] : 0.f;
+                df[e] = col < F_ ? (hh == 0 ? v0 : v1) : 0.f;
+            }
+            store_chunk(DF, nullptr, TM, 2 * hh, r, df);
+            store_chunk(DF, nullptr, TM, 2 * hh + 1, r, df + 8);
+        }
+        prefetch((long long)tile + gridDim.x);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm_kmajor<1>(tmem, DF, nullptr, wbt, nullptr, NB, CT, CT);
+            mma_commit(&bar);
+            bulk_s2g(st + OFF_DF, DF, SZ_DF);
+            bulk_commit();
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        store_dcomps_row<DC16>(lane_addr, hh, live, row, dcomps_out);
+        if (tid == 0) bulk_wait_read0();       // DF has left shared memory
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (tid == 0) bulk_wait0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace jt
 
 using namespace jt;
@@ -398,7 +462,7 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
     int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     if (int rc = set_smem(head_bwd_data_kernel<false>, BwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_data_kernel<true>, BwdSmem::total)) return rc;
-    if (int rc = set_smem(head_bwd_wgrad_kernel, WG_STAGES * WG_STAGE_BYTES)) return rc;
+    if (int rc = set_smem(head_bwd_wgrad_kernel<0, 4>, WG_STAGES * WG_STAGE_BYTES)) return rc;
     g_launches += 2;
     if (dcomps_bf16)
         head_bwd_data_kernel<true><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
@@ -406,8 +470,29 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
     else
         head_bwd_data_kernel<false><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
                                                                             fea_progress, dcomps, static_cast<unsigned char*>(stage));
-    head_bwd_wgrad_kernel<<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(static_cast<const unsigned char*>(stage),
-                                                                              n_dev, n_max, gWb, gW1, gb1, gW2, gb2,
-                                                                              gW3, gb3);
+    head_bwd_wgrad_kernel<0, 4><<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(
+        static_cast<const unsigned char*>(stage), n_dev, n_max, gWb, gW1, gb1, gW2, gb2, gW3, gb3);
+    JT_RETURN_LAUNCH();
+}
+
+extern "C" int jt_sh_bwd_tc(const float* dout, const float* featdir, int ldf, const float* Wb, const int* n_dev,
+                            int n_max, void* dcomps, int dcomps_bf16, void* stage, float* gWb, cudaStream_t stream) {
+    JT_CHECK_ARG(dout && featdir && Wb && dcomps && stage && gWb && ldf >= 32 && ldf % 4 == 0);
+    JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
+    if (n_max <= 0) return JT_OK;
+    long long tiles = ((long long)n_max + TM - 1) / TM;
+    int grid_d = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+    int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    if (int rc = set_smem(sh_bwd_data_kernel<false>, ShBwdSmem::total)) return rc;
+    if (int rc = set_smem(sh_bwd_data_kernel<true>, ShBwdSmem::total)) return rc;
+    if (int rc = set_smem(head_bwd_wgrad_kernel<3, 1>, WG_STAGES * WG_STAGE_BYTES)) return rc;
+    g_launches += 2;
+    unsigned char* st = static_cast<unsigned char*>(stage);
+    if (dcomps_bf16)
+        sh_bwd_data_kernel<true><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
+    else
+        sh_bwd_data_kernel<false><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
+    head_bwd_wgrad_kernel<3, 1><<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(st, n_dev, n_max, gWb, nullptr, nullptr,
+                                                                                   nullptr, nullptr, nullptr, nullptr);
     JT_RETURN_LAUNCH();
 }

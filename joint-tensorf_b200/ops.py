@@ -233,6 +233,23 @@ def app_basis_fwd_tc(split, fs, samp, aidx, sidx, rays_d, n_samples, normalize_d
                                              _p(featdir), _p(stage), _stream()), "jt_app_basis_fwd_tc")
 
 
+def app_basis_sh_fwd_tc(split, fs, samp, aidx, sidx, rays_d, n_samples, normalize_dir, wb, n_dev, n_max, featdir, rgb,
+                        stage=None):
+    """appearance gather + basis_mat + SHRender in one kernel -> rgb [A][4]; featdir [A][32] keeps the view dir."""
+    with TIMER.span("app_basis_sh_fwd_tc"):
+        check(_lib.lib().jt_app_basis_sh_fwd_tc(split, fs.ptrs, fs.dims, _p(samp), _p(aidx), _p(sidx), _p(rays_d),
+                                                int(n_samples), int(normalize_dir), _p(wb), _p(n_dev), int(n_max),
+                                                _p(featdir), _p(rgb), _p(stage), _stream()), "jt_app_basis_sh_fwd_tc")
+
+
+def sh_bwd_tc(dout, featdir, wb, n_dev, n_max, dcomps, stage, g_basis):
+    """g_basis [27][144] zero-initialised by the caller (accumulated)."""
+    with TIMER.span("sh_bwd_tc"):
+        check(_lib.lib().jt_sh_bwd_tc(_p(dout), _p(featdir), int(featdir.shape[1]), _p(wb), _p(n_dev), int(n_max),
+                                      _p(dcomps), int(dcomps.dtype == torch.bfloat16), _p(stage), _p(g_basis),
+                                      _stream()), "jt_sh_bwd_tc")
+
+
 def head_mlp_fwd_tc(split, featdir, w1, b1, w2, b2, w3, b3, n_dev, n_max, fprog, vprog, rgb, stage=None):
     with TIMER.span("head_mlp_fwd_tc"):
         check(_lib.lib().jt_head_mlp_fwd_tc(split, _p(featdir), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),

@@ -56,8 +56,10 @@ def tc_supported(cfg, afs=None, raise_if_not=False):
     hidden 64, fea_pe = view_pe = 2, 144 appearance components."""
     ok = (cfg.shading == "MLP_Fea" and cfg.app_dim == 27 and cfg.hidden == 64 and cfg.fea_pe == 2 and
           cfg.view_pe == 2 and (afs is None or afs.ctot == 144))
+    ok = ok or (cfg.shading == "SH" and cfg.app_dim == 27 and (afs is None or afs.ctot == 144))
     if not ok and raise_if_not:
-        raise _lib.JtError("head='tc' needs MLP_Fea / app_dim 27 / hidden 64 / pe 2 / 144 components; use head='fp32'")
+        raise _lib.JtError("head='tc' needs MLP_Fea (hidden 64, pe 2) or SH shading with app_dim 27 and 144 "
+                           "components; use head='fp32'")
     return ok
 
 
@@ -191,10 +193,14 @@ class VMRender(torch.autograd.Function):
             train = any(ctx.needs_input_grad)
             feat = torch.empty((cap, 32), device=dev)             # feat 0..26 | 0 | view dir 28..30 | 0
             ws["stage"] = ops.head_tc_stage(cap, dev) if train else None
-            ops.app_basis_fwd_tc(cfg.tc_fwd_split, afs, comp.samp, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w,
-                                 a_count, cap, feat, ws["stage"])
-            ops.head_mlp_fwd_tc(cfg.tc_fwd_split, feat, *head, a_count, cap, cfg.fea_prog, cfg.view_prog, rgb,
-                                ws["stage"])
+            if cfg.shading == "SH":
+                ops.app_basis_sh_fwd_tc(cfg.tc_fwd_split, afs, comp.samp, aidx, comp.sidx, rays_d, S, cfg.ndc,
+                                        basis_w, a_count, cap, feat, rgb, ws["stage"])
+            else:
+                ops.app_basis_fwd_tc(cfg.tc_fwd_split, afs, comp.samp, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w,
+                                     a_count, cap, feat, ws["stage"])
+                ops.head_mlp_fwd_tc(cfg.tc_fwd_split, feat, *head, a_count, cap, cfg.fea_prog, cfg.view_prog, rgb,
+                                    ws["stage"])
         else:
             comps = torch.empty((cap, afs.ctot), device=dev)
             ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
@@ -268,7 +274,9 @@ class VMRender(torch.autograd.Function):
 
         # tensor-core head: dcomps crosses HBM as bf16 (its GEMM operands are bf16 already)
         dcomps = torch.empty((cap, afs.ctot), device=dev, dtype=torch.bfloat16 if cfg.head == "tc" else torch.float32)
-        if cfg.head == "tc":
+        if cfg.head == "tc" and cfg.shading == "SH":
+            ops.sh_bwd_tc(dout, b["feat"], b["basis_w"], b["a_count"], cap, dcomps, ws["stage"], g_basis)
+        elif cfg.head == "tc":
             w1, b1, w2, b2, w3, b3 = b["head"]
             ops.head_bwd_tc(dout, b["feat"], b["basis_w"], w1, w2, w3, b["a_count"], cap, cfg.fea_prog, dcomps,
                             ws["stage"], (g_basis, *head_grads))

@@ -42,6 +42,10 @@ CASES = {
                        n_rays=64, train=False, blur=None, mask=True),
     "sh": dict(grid=[24, 24, 24], dens=[8] * 3, app=[12] * 3, app_dim=27, shading="SH", hidden=0,
                n_rays=64, train=True, blur=None),
+    # BASELINE configs[1] component counts (16 / 48 per plane, app_dim 27, SH shading): the shape the
+    # tensor-core SH path (jt_app_basis_sh_fwd_tc / jt_sh_bwd_tc) is specialised for
+    "sh_vm48": dict(grid=[32, 32, 32], dens=[16] * 3, app=[48] * 3, app_dim=27, shading="SH", hidden=0,
+                    n_rays=96, train=True, blur=None, dens_scale=3.5),
     "ndc_weakview": dict(grid=[24, 28, 24], dens=[16] * 3, app=[20] * 3, app_dim=20, shading="MLP_Fea_WeakView",
                          hidden=32, n_rays=64, train=True, blur=None, ndc=True, dens_scale=0.12),
     "ndc_weakview_blur": dict(grid=[24, 28, 24], dens=[16] * 3, app=[20] * 3, app_dim=20, shading="MLP_Fea_WeakView",

@@ -84,6 +84,61 @@ def test_tensor_core_head_on_reference_golden():
         assert rel_err(out["grads"][k].cpu(), ref) <= TC_GRAD_REL_TOL, (k, rel_err(out["grads"][k].cpu(), ref))
 
 
+def test_tensor_core_sh_on_reference_golden():
+    """sh_vm48 golden (16/48 comps, app_dim 27, SH shading = BASELINE configs[1]) through the fused
+    gather + basis_mat + SHRender kernel and the tcgen05 SH backward."""
+    g = load_golden("sh_vm48")
+    out = run_module_on_golden(g, DEV, head="tc")
+    assert (out["rgb"].cpu() - g["rgb"]).abs().max() <= ABS_TOL
+    assert (out["acc"].cpu() - g["acc"]).abs().max() <= ABS_TOL
+    assert (out["depth"].cpu() - g["depth"]).abs().max() <= ABS_TOL
+    assert rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]) <= TC_GRAD_REL_TOL
+    assert rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]) <= TC_GRAD_REL_TOL
+    for k, ref in g["grads"].items():
+        assert rel_err(out["grads"][k].cpu(), ref) <= TC_GRAD_REL_TOL, (k, rel_err(out["grads"][k].cpu(), ref))
+
+
+@pytest.mark.parametrize("head", ["fp32", "tc"])
+def test_midsize_sh_against_oracle(head):
+    """128^3, 16/48 comps, SH shading, 300 rays (a ragged last tile): CUDA path vs the CPU oracle;
+    the inference call (no staging, no autograd) must reproduce the training colours."""
+    kw, run = jt.synth.config("cfg1")
+    kw["shadingMode"] = "SH"
+    torch.manual_seed(0)
+    m = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), DEV, **kw)
+    m.head_precision = head
+    gtol = GRAD_REL_TOL if head == "fp32" else TC_GRAD_REL_TOL
+    with torch.no_grad():
+        for i in range(3):
+            m.density_plane[i].mul_(4.0)
+            m.density_line[i].mul_(4.0)
+    n = 300
+    o, d, _ = jt.synth.blender_rays(n, 10, seed=5)
+    S = run["n_samples"]
+    jit = torch.rand(n, 1, generator=torch.Generator().manual_seed(11))
+    params = {k: v.detach().cpu().contiguous().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    field = vo.Field(aabb=m.aabb.cpu(), grid=[128] * 3, params=params, near_far=[2.0, 6.0], step_ratio=0.5,
+                     density_shift=-10.0, distance_scale=25.0, weight_thres=1e-6, act="softplus", shading="SH")
+    oc, dc = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    rgb_ref, depth_ref, acc_ref = vo.render(field, oc, dc, n_samples=S, white_bg=True, jitter=jit)
+    w = torch.rand(n, 3, generator=torch.Generator().manual_seed(4))
+    (rgb_ref * w).sum().backward()
+    og, dg = o.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+    fkw = dict(white_bg=True, is_train=True, N_samples=S, jitter=jit.to(DEV), bg_coin=False)
+    rgb, depth, acc = m.forward(default_opt("SH"), og, dg, **fkw)
+    (rgb * w.to(DEV)).sum().backward()
+    assert (rgb.cpu() - rgb_ref).abs().max() <= ABS_TOL
+    assert (acc.cpu() - acc_ref).abs().max() <= ABS_TOL
+    assert (depth.cpu() - depth_ref).abs().max() <= ABS_TOL
+    assert rel_err(og.grad.cpu(), oc.grad) <= gtol
+    assert rel_err(dg.grad.cpu(), dc.grad) <= gtol
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad.cpu(), params[k].grad) <= gtol, (k, rel_err(p.grad.cpu(), params[k].grad))
+    with torch.no_grad():
+        rgb_inf, _, _ = m.forward(default_opt("SH"), o.to(DEV), d.to(DEV), **fkw)
+    assert torch.equal(rgb_inf, rgb.detach())
+
+
 @pytest.mark.parametrize("blur", [None, (0.1, 0.15)])
 @pytest.mark.parametrize("head", ["fp32", "tc"])
 def test_midsize_against_oracle(blur, head):

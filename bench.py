@@ -4,10 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            (own arm, B200 kernels)
     python bench.py --impl reference --gpus N ...            (reference arm: CPU port)
 
-Workload (BASELINE.json configs[1], "cfg2"): TensoRF-VM 300^3 grid, density 3x16 /
-appearance 3x48 components, app_dim 27, MLP_Fea shading head, 4096-ray batch, S=1000
-samples per ray, forward + backward to all factor / head / ray gradients. Synthetic
-Blender-shaped rays and random-init factors (joint_tensorf_b200.synth).
+Workload (BASELINE.json configs[1], "cfg2_sh"): TensoRF-VM 300^3 grid, density 3x16 /
+appearance 3x48 components, app_dim 27, SH shading, 4096-ray batch, S=1000 samples per
+ray, forward + backward to all factor / basis / ray gradients. Synthetic Blender-shaped
+rays and random-init factors (joint_tensorf_b200.synth). The same field with the
+MLP_Fea shading head (`--workload cfg2`, the head of the BAT VM_MLP configs) is timed in
+the same run and reported under "also".
 
 A step = one training iteration without the optimizer (SURVEY.md section 8d timing
 protocol): se3_refine + fixed poses -> rays of the sampled pixels (jt_pose_rays_fwd) ->
@@ -38,7 +40,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg2_sh",
+                    help="cfg2_sh = BASELINE.json configs[1] (300^3, 3x16 / 3x48 comps, app_dim 27, SH shading); "
+                         "cfg2 = same field with the MLP_Fea head; cfg1 = 128^3; cfg4 = LLFF NDC 617x687x617")
+    ap.add_argument("--no-also", action="store_true",
+                    help="skip the second head variant of the 300^3 field (cfg2 <-> cfg2_sh) timed after the headline")
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--blur", type=float, default=0.0, help="c2f blur parameter (0 = off, cfg3 uses 0.15)")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays in the bounded CPU-baseline sample")
@@ -212,6 +218,11 @@ def time_aten_gpu(workload, n_rays, steps, warmup, dev):
     return n_rays / sec, sec
 
 
+def synth_describe(workload, n_rays=None):
+    from joint_tensorf_b200 import synth
+    return synth.describe(workload, n_rays)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,8 +234,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, S=1000, "
-                               f"{n}-ray sample of the 4096-ray batch, fwd+bwd", "blur": args.blur},
+        "config": {"workload": synth_describe(args.workload) + f", {n}-ray sample of the {args.rays}-ray batch, fwd+bwd",
+                   "blur": args.blur},
         "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} of 4096 rays per step, {steps} steps, oracle/vm_oracle.py (torch CPU, "
                                    f"{cores} threads)"},
@@ -239,9 +250,12 @@ def algorithmic_bytes(name, V, A, cd, ca, ctot_a):
     s = 4
     dens_f = V * (18 * cd * s + 16)                 # 3 x (4+2) taps x C_d x 4 B + coords in + feature out
     app_f = A * (18 * ca * s + 12 + 4 * ctot_a)     # taps + coords + component row out (un-fused)
+    app_fused = A * (18 * ca * s + 12)              # taps + coords; the component row stays on chip
     table = {
         "vm_density_fwd": dens_f,
         "vm_app_fwd": app_f,
+        "app_basis_fwd_tc": app_fused + A * 128,    # + feat/dir row out
+        "app_basis_sh_fwd_tc": app_fused + A * 32,  # + rgb and view direction out
         "vm_density_bwd": V * (3 * 18 * cd * s + 4 + 16),
         "vm_app_bwd": A * (3 * 18 * ca * s + 4 * ctot_a + 16),
     }
@@ -267,6 +281,8 @@ def gemm_flops(name, A, F, ctot, in_dim, H):
         # fused tensor-core head: basis + 3 layers forward; data + weight gradients backward
         "head_fwd_tc": 2 * A * (F * ctot + in_dim * H + H * H + H * 3),
         "head_bwd_tc": 4 * A * (F * ctot + in_dim * H + H * H + H * 3),
+        "head_mlp_fwd_tc": 2 * A * (in_dim * H + H * H + H * 3),
+        "sh_bwd_tc": 4 * A * F * ctot,
     }
     return table.get(name)
 
@@ -304,17 +320,26 @@ def own_arm(args):
     # Pose side of the step (SURVEY 8d protocol): 32 hemisphere views, pose noise N(0, 0.15^2) composed into the
     # fixed pose (bat.py:34,346-348), se3_refine = 0 and trainable (bat.py:350), 128 pixels shared by all views
     # (nerf.py:657-658) -> N = 4096 rays generated by jt_pose_rays_fwd, gradients back to se3_refine.
-    n_views = 32
-    H_img = W_img = 800
+    # LLFF (cfg4): 8 forward-facing views = small rigid motions of the identity, 1008x756, focal 0.85 W, rays
+    # converted to NDC (camera.py:303-340) inside the same kernel.
+    ndc = bool(run["ndc"])
+    n_views = 8 if ndc else 32
+    H_img, W_img = (756, 1008) if ndc else (800, 800)
     R_pix = max(1, N // n_views)
     N = n_views * R_pix
-    gt_pose, intr = jt.synth.blender_views(n_views, (H_img, W_img), seed=1 + rank)
-    g_noise = torch.Generator().manual_seed(50 + rank)
-    pose_noise = 0.15 * torch.randn((n_views, 6), generator=g_noise)
-    base_pose = jt.camera.refined_pose(pose_noise.to(dev), gt_pose.to(dev))
+    if ndc:
+        gt_pose, intr = jt.synth.llff_views(n_views, (H_img, W_img), seed=1 + rank)
+        base_pose = gt_pose.to(dev)
+    else:
+        gt_pose, intr = jt.synth.blender_views(n_views, (H_img, W_img), seed=1 + rank)
+        g_noise = torch.Generator().manual_seed(50 + rank)
+        pose_noise = 0.15 * torch.randn((n_views, 6), generator=g_noise)
+        base_pose = jt.camera.refined_pose(pose_noise.to(dev), gt_pose.to(dev))
     intr_inv_d = intr.inverse().to(dev)
+    intr_d = intr.to(dev) if ndc else None       # convert_NDC reads the focal length / principal point
     se3_refine = torch.nn.Parameter(torch.zeros((n_views, 6), device=dev))
-    cam_opt = jt.options.Namespace(H=H_img, W=W_img, camera=dict(model="perspective", ndc=False), arch=dict())
+    cam_opt = jt.options.Namespace(H=H_img, W=W_img, camera=dict(model="perspective", ndc=ndc),
+                                   arch=dict(ndc_near_plane=1.0) if ndc else dict())
     pix_h = torch.randperm(H_img * W_img, generator=torch.Generator().manual_seed(7 + rank))[:R_pix].to(torch.int32)
     tgt_h = torch.rand(N, 3, generator=torch.Generator().manual_seed(100 + rank))
     pix_h, tgt_h = pix_h.pin_memory(), tgt_h.pin_memory()
@@ -331,17 +356,22 @@ def own_arm(args):
     model.grad_sync = sync
     inv_world = 1.0 / world
 
-    def step(pix, tgt, reduce=True):
-        for p in params:
-            p.grad = None
-        model.grad_sync = sync if reduce else None
-        center, ray = jt.camera.get_center_and_ray(cam_opt, base_pose, intr_inv_d, ray_idx=pix, se3_refine=se3_refine)
-        rgb, depth, acc = model(opt, center.view(-1, 3), ray.view(-1, 3), **fkw)
-        loss = ((rgb - tgt) ** 2).mean()
-        (loss * inv_world if world > 1 else loss).backward()
-        if sync is not None and reduce:
-            sync.finish([se3_refine])
-        return loss
+    def make_step(model, opt, params):
+        def step(pix, tgt, reduce=True):
+            for p in params:
+                p.grad = None
+            model.grad_sync = sync if reduce else None
+            center, ray = jt.camera.get_center_and_ray(cam_opt, base_pose, intr_inv_d, ray_idx=pix, intr=intr_d,
+                                                       se3_refine=se3_refine)
+            rgb, depth, acc = model(opt, center.view(-1, 3), ray.view(-1, 3), **fkw)
+            loss = ((rgb - tgt) ** 2).mean()
+            (loss * inv_world if world > 1 else loss).backward()
+            if sync is not None and reduce:
+                sync.finish([se3_refine])
+            return loss
+        return step
+
+    step = make_step(model, opt, params)
 
     def step_e2e():
         pix = pix_h.to(dev, non_blocking=True)
@@ -427,17 +457,18 @@ def own_arm(args):
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": ach / tf_peak, "traffic": NCU_DRAM_BYTES.get(top), "peak_source": peak_src,
                     "ms_per_launch": per_launch_ms}
-        gather = sum(breakdown.get(k, 0.0) for k in ("vm_density_fwd", "vm_app_fwd", "vm_density_bwd", "vm_app_bwd"))
-        gbytes = sum(algorithmic_bytes(k, V, A, cd, ca, sum(model.app_n_comp))
-                     for k in ("vm_density_fwd", "vm_app_fwd", "vm_density_bwd", "vm_app_bwd"))
+        gk = [k for k in ("vm_density_fwd", "vm_app_fwd", "app_basis_fwd_tc", "app_basis_sh_fwd_tc", "vm_density_bwd",
+                          "vm_app_bwd") if k in breakdown]
+        gather = sum(breakdown[k] for k in gk)
+        gbytes = sum(algorithmic_bytes(k, V, A, cd, ca, sum(model.app_n_comp)) for k in gk)
         if roof is not None and gather > 0:
             roof["vm_gather_fwd_bwd"] = {"ms": gather, "achieved": gbytes / (gather * 1e-3) / 1e9,
-                                         "frac": gbytes / (gather * 1e-3) / 1e9 / hbm_peak, "V": V, "A": A}
+                                         "frac": gbytes / (gather * 1e-3) / 1e9 / hbm_peak, "V": V, "A": A,
+                                         "kernels": gk}
 
     # second half of BASELINE.json's metric: one 800x800 frame (640 000 rays, cfg2 field, is_train=False, no
     # blur) rendered like the reference's render_by_slices (model/nerf.py:728-740), rays resident on the device
-    render = None
-    if rank == 0 and not args.no_render:
+    def time_render(mdl, mopt):
         n_pix = H_img * W_img
         f_pose, f_kinv = gt_pose[:1].to(dev), intr_inv_d[:1]
         rkw = dict(white_bg=run["white_bg"], is_train=False, ndc_ray=run["ndc"], N_samples=S)
@@ -448,21 +479,49 @@ def own_arm(args):
             outs = []
             with torch.no_grad():
                 for c in range(0, n_pix, chunk):
-                    ce, ra = jt.camera.get_center_and_ray(cam_opt, f_pose, f_kinv, pix_base=c, n_rays=min(chunk, n_pix - c))
-                    outs.append(model(opt, ce.view(-1, 3), ra.view(-1, 3), **rkw)[0])
+                    ce, ra = jt.camera.get_center_and_ray(cam_opt, f_pose, f_kinv, pix_base=c, n_rays=min(chunk, n_pix - c),
+                                                          intr=intr_d[:1] if ndc else None)
+                    outs.append(mdl(mopt, ce.view(-1, 3), ra.view(-1, 3), **rkw)[0])
             return torch.cat(outs)
 
         render_frame()
         torch.cuda.synchronize()
+        frames = 3
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush.fill_(1.0)
         s_ev.record()
-        img = render_frame()
+        for _ in range(frames):
+            img = render_frame()
         e_ev.record()
         torch.cuda.synchronize()
-        fms = s_ev.elapsed_time(e_ev)
-        render = {"ms_per_frame": fms, "rays_per_s": n_pix / (fms * 1e-3), "frame": "800x800", "rays_per_call": chunk,
-                  "finite": bool(torch.isfinite(img).all())}
+        fms = s_ev.elapsed_time(e_ev) / frames
+        return {"ms_per_frame": fms, "rays_per_s": n_pix / (fms * 1e-3), "frame": f"{W_img}x{H_img}",
+                "frames_timed": frames, "rays_per_call": chunk, "finite": bool(torch.isfinite(img).all())}
+
+    render = time_render(model, opt) if rank == 0 and not args.no_render else None
+
+    # the other shading head on the same 300^3 field (cfg2_sh <-> cfg2): same rays, same protocol, timed after the
+    # headline so that it cannot disturb it. Single-GPU runs only.
+    also = None
+    other = {"cfg2_sh": "cfg2", "cfg2": "cfg2_sh"}.get(args.workload)
+    if rank == 0 and world == 1 and other and not args.no_also and args.blur == 0:
+        kw_o, _ = jt.synth.config(other)
+        kw_o = dict(kw_o)
+        torch.manual_seed(0)
+        model_o = jt.B200_VMSplit(torch.tensor(kw_o.pop("aabb")), kw_o.pop("gridSize"), dev, **kw_o)
+        model_o.head_precision = args.head
+        opt_o = default_opt(model_o.shadingMode, run["ndc"])
+        step_o = make_step(model_o, opt_o, [p for p in model_o.parameters()] + [se3_refine])
+        for _ in range(max(args.warmup, 3)):
+            step_o(pix_d, tgt_d, reduce=False)
+        torch.cuda.synchronize()
+        ms_o = timed(lambda: step_o(pix_d, tgt_d, reduce=False), args.steps)
+        also = {"workload": jt.synth.describe(other, N), "value": N * args.steps / (ms_o * 1e-3), "unit": UNIT,
+                "ms_per_step": ms_o / args.steps, "steps": args.steps}
+        if not args.no_render:
+            also["render_800x800"] = time_render(model_o, opt_o)
+        del model_o, step_o
+        torch.cuda.empty_cache()
 
     # next rows of SURVEY 8f, timed after everything above because the optimiser changes the parameters:
     # 8f-2 a full training iteration = the step above + density_L1 regulariser (Blender weight 8e-5, TV weights 0,
@@ -550,11 +609,11 @@ def own_arm(args):
             "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.head == "fp32" else "f32 (shading-head GEMMs on tcgen05: bf16 operands, f32 accumulate)",
+            "dtype": "f32" if args.head == "fp32" else "f32 (basis/shading GEMMs on tcgen05: bf16 operands, f32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: TensoRF-VM 300^3, 3x16/3x48 comps, app_dim 27, MLP_Fea, "
-                                   f"S={S}, {N} rays/GPU ({n_views} views x {R_pix} pixels, rays generated from se3_refine + pose "
-                                   f"inside the step), fwd+bwd to factor/head/se3 gradients, optimizer step excluded",
+            "config": {"workload": jt.synth.describe(args.workload, N) +
+                                   f" ({n_views} views x {R_pix} pixels, rays generated from se3_refine + pose inside the step), "
+                                   "fwd+bwd to factor/basis/head/se3 gradients, optimizer step excluded",
                        "head": args.head,
                        "head_arith": "forward: hi+lo split bf16 operands (3 MMAs per product, fp32-class, rgb within 1e-4); "
                                      "backward: bf16 operands, f32 accumulate (gradients within 2e-2 rel)",
@@ -572,6 +631,8 @@ def own_arm(args):
             line["kernel_ms_per_step"] = breakdown
         if render is not None:
             line["render_800x800"] = render
+        if also is not None:
+            line["also"] = also
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if aten is not None:

@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(NTB, 2) head_bwd_data_kernel(
 constexpr int WG_STAGES = 3;
 constexpr int WG_A_REGION = 32768;            // the M=128 A descriptor spans 16 groups x 2048 B
 constexpr int WG_STAGE_BYTES = WG_A_REGION + SZ_A1;
+// basis_mat alone (SH shading): stages of [A region | component tile]
+constexpr int WG_SH_STAGES = 3;
+constexpr int WG_SH_STAGE_BYTES = WG_A_REGION + SZ_A0;
 
 struct WGroup { int a_off, a_bytes, b_off, b_bytes, n, col; };
 __device__ __forceinline__ WGroup wgroup(int g) {
@@ -245,7 +248,7 @@ __device__ __forceinline__ WGroup wgroup(int g) {
 
 // Groups [G0, G0 + NG) of wgroup() are accumulated: <0, 4> is the MLP_Fea head + basis_mat,
 // <3, 1> basis_mat alone (SH shading: jt_sh_bwd_tc).
-template <int G0, int NG>
+template <int G0, int NG, int STAGES, int STAGE_BYTES>
 __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char* __restrict__ stage,
                                                             const int* __restrict__ n_dev, int n_fixed,
                                                             float* __restrict__ gWb, float* __restrict__ gW1,
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
                                                             float* __restrict__ gb2, float* __restrict__ gW3,
                                                             float* __restrict__ gb3) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[WG_STAGES], empty[WG_STAGES], done;
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = n_dev ? *n_dev : n_fixed;
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&done, 1);
         mbar_fence_init();
     }
@@ -274,23 +277,23 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
 
     if (warp == 0 && lane == 0) {                 // ---- TMA producer
         for (int i = 0; i < items; ++i) {
-            const int s = i % WG_STAGES, round = i / WG_STAGES;
+            const int s = i % STAGES, round = i / STAGES;
             mbar_wait(&empty[s], (round & 1) ^ 1);
             const int tile = blockIdx.x + (i / NG) * gridDim.x;
             const WGroup g = wgroup(G0 + i % NG);
             const unsigned char* src = stage + (size_t)tile * STAGE_TILE_BYTES;
-            unsigned char* dst = smem + s * WG_STAGE_BYTES;
+            unsigned char* dst = smem + s * STAGE_BYTES;
             mbar_expect_tx(&full[s], (uint32_t)(g.a_bytes + g.b_bytes));
             bulk_g2s(dst, src + g.a_off, g.a_bytes, &full[s]);
             bulk_g2s(dst + WG_A_REGION, src + g.b_off, g.b_bytes, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {          // ---- MMA issuer
         for (int i = 0; i < items; ++i) {
-            const int s = i % WG_STAGES, round = i / WG_STAGES;
+            const int s = i % STAGES, round = i / STAGES;
             mbar_wait(&full[s], round & 1);
             tc_fence_after();
             const WGroup g = wgroup(G0 + i % NG);
-            const uint32_t a = smem_u32(smem + s * WG_STAGE_BYTES), b = a + WG_A_REGION;
+            const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + WG_A_REGION;
             const uint32_t idesc = idesc_bf16(128, g.n, 1, 1);
 #pragma unroll
             for (int ks = 0; ks < TM / 16; ++ks)       // K = 128 sample rows, 16 per MMA = 256 B
@@ -354,7 +357,9 @@ struct ShBwdSmem {
     static constexpr int WBT = tile_bytes(CT, NB);
     static constexpr int off_wbt = 0, off_df = off_wbt + WBT;
     static constexpr int used = off_df + SZ_DF;
-    // two CTAs per SM at most: each allocates 256 of the SM's 512 TMEM columns
+    // padded to 100 KB: at most two CTAs share an SM, each allocates 256 of its 512 TMEM columns. (Running the
+    // density scatter next to this kernel on a second stream was measured: the kernels slow each other down by
+    // as much as they overlap, 3.48 -> 3.39 ms at best, 3.75 ms at worst; not kept.)
     static constexpr int total = used > 100 * 1024 ? used : 100 * 1024;
 };
 
@@ -462,7 +467,7 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
     int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     if (int rc = set_smem(head_bwd_data_kernel<false>, BwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_data_kernel<true>, BwdSmem::total)) return rc;
-    if (int rc = set_smem(head_bwd_wgrad_kernel<0, 4>, WG_STAGES * WG_STAGE_BYTES)) return rc;
+    if (int rc = set_smem(head_bwd_wgrad_kernel<0, 4, WG_STAGES, WG_STAGE_BYTES>, WG_STAGES * WG_STAGE_BYTES)) return rc;
     g_launches += 2;
     if (dcomps_bf16)
         head_bwd_data_kernel<true><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
@@ -470,7 +475,7 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
     else
         head_bwd_data_kernel<false><<<grid_d, NTB, BwdSmem::total, stream>>>(dout, feat, ldf, Wb, W1, W2, W3, n_dev, n_max,
                                                                             fea_progress, dcomps, static_cast<unsigned char*>(stage));
-    head_bwd_wgrad_kernel<0, 4><<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(
+    head_bwd_wgrad_kernel<0, 4, WG_STAGES, WG_STAGE_BYTES><<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(
         static_cast<const unsigned char*>(stage), n_dev, n_max, gWb, gW1, gb1, gW2, gb2, gW3, gb3);
     JT_RETURN_LAUNCH();
 }
@@ -485,14 +490,14 @@ extern "C" int jt_sh_bwd_tc(const float* dout, const float* featdir, int ldf, co
     int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     if (int rc = set_smem(sh_bwd_data_kernel<false>, ShBwdSmem::total)) return rc;
     if (int rc = set_smem(sh_bwd_data_kernel<true>, ShBwdSmem::total)) return rc;
-    if (int rc = set_smem(head_bwd_wgrad_kernel<3, 1>, WG_STAGES * WG_STAGE_BYTES)) return rc;
+    if (int rc = set_smem(head_bwd_wgrad_kernel<3, 1, WG_SH_STAGES, WG_SH_STAGE_BYTES>, WG_SH_STAGES * WG_SH_STAGE_BYTES)) return rc;
     g_launches += 2;
     unsigned char* st = static_cast<unsigned char*>(stage);
     if (dcomps_bf16)
         sh_bwd_data_kernel<true><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
     else
         sh_bwd_data_kernel<false><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
-    head_bwd_wgrad_kernel<3, 1><<<grid_w, TM, WG_STAGES * WG_STAGE_BYTES, stream>>>(st, n_dev, n_max, gWb, nullptr, nullptr,
-                                                                                   nullptr, nullptr, nullptr, nullptr);
+    head_bwd_wgrad_kernel<3, 1, WG_SH_STAGES, WG_SH_STAGE_BYTES><<<grid_w, TM, WG_SH_STAGES * WG_SH_STAGE_BYTES, stream>>>(
+        st, n_dev, n_max, gWb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     JT_RETURN_LAUNCH();
 }

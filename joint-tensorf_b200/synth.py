@@ -92,6 +92,26 @@ def frame_rays(view=0, hw=(800, 800), focal=1111.1, radius=4.0, seed=2):
     return o.contiguous(), d.contiguous()
 
 
+def llff_views(n_views=8, hw=(756, 1008), seed=1):
+    """The cameras of `llff_ndc_rays` as matrices: world-to-camera poses [B,3,4] (small random rigid
+    motions of the identity) and intrinsics [B,3,3] with focal 0.85 W."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = hw
+    focal = 0.85 * w
+    rv = 0.05 * torch.randn((n_views, 3), generator=g)
+    tv = 0.05 * torch.randn((n_views, 3), generator=g)
+    ang = rv.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    k = rv / ang
+    kx = torch.zeros(n_views, 3, 3)
+    kx[:, 0, 1], kx[:, 0, 2], kx[:, 1, 0] = -k[:, 2], k[:, 1], k[:, 2]
+    kx[:, 1, 2], kx[:, 2, 0], kx[:, 2, 1] = -k[:, 0], -k[:, 1], k[:, 0]
+    a = ang[..., None]
+    rot = torch.eye(3)[None] + torch.sin(a) * kx + (1 - torch.cos(a)) * (kx @ kx)
+    pose = torch.cat([rot, tv[..., None]], dim=-1)
+    intr = torch.tensor([[focal, 0.0, w / 2], [0.0, focal, h / 2], [0.0, 0.0, 1.0]])[None].repeat(n_views, 1, 1)
+    return pose.contiguous(), intr.contiguous()
+
+
 def llff_ndc_rays(n_rays=4096, n_views=8, hw=(756, 1008), seed=1, near=1.0):
     """Forward-facing NDC rays (cfg4). Poses are small random rigid motions of
     the identity; rays are shifted to the near plane and projected as in
@@ -127,6 +147,19 @@ def llff_ndc_rays(n_rays=4096, n_views=8, hw=(756, 1008), seed=1, near=1.0):
 
 
 # ---------------------------------------------------------------- workload configurations
+def describe(name, n_rays=None):
+    """One-line description of a workload for bench.py's `config.workload`."""
+    kw, run = config(name)
+    g = kw["gridSize"]
+    grid = f"{g[0]}^3" if g[0] == g[1] == g[2] else "x".join(str(x) for x in g)
+    head = {"SH": "SH(deg 2) shading", "MLP_Fea": f"MLP_Fea {kw['featureC']} head",
+            "MLP_Fea_WeakView": f"MLP_Fea_WeakView {kw['featureC']} head"}[kw["shadingMode"]]
+    rays = "LLFF forward-facing NDC rays" if run["ndc"] else "Blender-shaped rays"
+    s = (f"{name}: TensoRF-VM {grid}, density 3x{kw['density_n_comp'][0]} / appearance 3x{kw['appearance_n_comp'][0]} "
+         f"comps, app_dim {kw['app_dim']}, {head}, S={run['n_samples']}, {rays}")
+    return s + (f", {n_rays} rays/GPU" if n_rays else "")
+
+
 def config(name):
     """Constructor keyword sets of the benchmark configurations.
     `n_samples` follows model/tensorf.py:449-461:

@@ -355,19 +355,23 @@ __global__ void __launch_bounds__(TM) head_bwd_wgrad_kernel(const unsigned char*
 // basis_mat weight gradient is group 3 of the shared TMA -> tcgen05 wgrad pipeline.
 struct ShBwdSmem {
     static constexpr int WBT = tile_bytes(CT, NB);
-    static constexpr int off_wbt = 0, off_df = off_wbt + WBT;
-    static constexpr int used = off_df + SZ_DF;
-    // padded to 100 KB: at most two CTAs share an SM, each allocates 256 of its 512 TMEM columns. (Running the
-    // density scatter next to this kernel on a second stream was measured: the kernels slow each other down by
-    // as much as they overlap, 3.48 -> 3.39 ms at best, 3.75 ms at worst; not kept.)
-    static constexpr int total = used > 100 * 1024 ? used : 100 * 1024;
+    static constexpr int OUT = TM * CT * 2;                     // dcomps tile, bf16 row-major = its global image
+    static constexpr int off_wbt = 0, off_df = off_wbt + WBT, off_out = off_df + 2 * SZ_DF;
+    // 91 KB: two CTAs per SM (each allocates 256 of the SM's 512 TMEM columns)
+    static constexpr int total = off_out + 2 * OUT;
 };
 
-template <bool DC16>
+__device__ __forceinline__ void bulk_wait_read_2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
+
+// dcomps leaves the SM as ONE bulk async store per tile: the 128 rows x 288 B of a tile are contiguous in
+// global memory, the threads only write their TMEM columns into a shared-memory image of it (per-thread
+// 16-byte global stores at a 288-byte row pitch kept the LSU queues full: lg_throttle, 0.33 ms). DF and
+// the output tile are double-buffered; the issuing thread waits for the bulk stores of two tiles ago
+// *before* it signals the MMA barrier, so passing that barrier also means both buffers are free.
 __global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ featdir,
                                                              int ldf, const float* __restrict__ Wb,
                                                              const int* __restrict__ n_dev, int n_fixed,
-                                                             void* __restrict__ dcomps_out,
+                                                             unsigned short* __restrict__ dcomps_out,
                                                              unsigned char* __restrict__ stage) {
     using L = ShBwdSmem;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -377,7 +381,6 @@ __global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __rest
     const int r = tid & (TM - 1), hh = tid >> 7;
     const int n = n_dev ? *n_dev : n_fixed;
     unsigned char* wbt = smem + L::off_wbt;
-    unsigned char* DF = smem + L::off_df;
 
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -389,6 +392,7 @@ __global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __rest
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
+    int buf = 0;
 
     float4 g4, d4;                     // dpre and view direction of the NEXT tile's row (prefetched)
     auto prefetch = [&](long long t) {
@@ -401,10 +405,11 @@ __global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __rest
     };
     prefetch(blockIdx.x);
 
-    for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
-        const int row = tile * TM + r;
-        const bool live = row < n;
+    for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x, buf ^= 1) {
+        const int rows = min(TM, n - tile * TM);
         unsigned char* st = stage + (size_t)tile * STAGE_TILE_BYTES;
+        unsigned char* DF = smem + L::off_df + buf * SZ_DF;
+        unsigned char* OUT = smem + L::off_out + buf * L::OUT;
         // ---- DF row: columns c*9+k = dpre[c] * Y_k, 27..31 = 0; this thread: columns [16 hh, 16 hh + 16)
         {
             const float d[3] = {d4.x, d4.y, d4.z};
@@ -429,16 +434,44 @@ __global__ void __launch_bounds__(NTB, 2) sh_bwd_data_kernel(const float* __rest
         if (tid == 0) {
             tc_fence_after();
             issue_gemm_kmajor<1>(tmem, DF, nullptr, wbt, nullptr, NB, CT, CT);
-            mma_commit(&bar);
             bulk_s2g(st + OFF_DF, DF, SZ_DF);
             bulk_commit();
+            // pending afterwards: at most OUT(t-1) and DF(t) -> DF(t-1) and OUT(t-2), the previous users of the
+            // buffers this tile's successor / this tile's epilogue write, have been read out of shared memory
+            bulk_wait_read_2();
+            mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1;
         tc_fence_after();
-        store_dcomps_row<DC16>(lane_addr, hh, live, row, dcomps_out);
-        if (tid == 0) bulk_wait_read0();       // DF has left shared memory
-        tc_fence_before();
+        // ---- dcomps row -> bf16 -> shared-memory image of the tile; hh = 0: columns [0,64) + [128,144), hh = 1: [64,128)
+        {
+            uint4* orow = reinterpret_cast<uint4*>(OUT + (size_t)r * (CT * 2));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float g[32];
+                const int c0 = 64 * hh + 32 * k;
+                tmem_ld32(lane_addr + c0, g);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    orow[c0 / 8 + q] = make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                                  pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7]));
+            }
+            if (hh == 0) {
+                float g[16];
+                tmem_ld16(lane_addr + 128, g);
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    orow[16 + q] = make_uint4(pack_bf16(g[8 * q], g[8 * q + 1]), pack_bf16(g[8 * q + 2], g[8 * q + 3]),
+                                              pack_bf16(g[8 * q + 4], g[8 * q + 5]), pack_bf16(g[8 * q + 6], g[8 * q + 7]));
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();                     // all tcgen05.ld of this tile are complete before the next MMAs
         __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(dcomps_out + (size_t)tile * TM * CT, OUT, (uint32_t)rows * (CT * 2));
+            bulk_commit();
+        }
     }
     if (tid == 0) bulk_wait0();
     tc_fence_before();
@@ -483,20 +516,18 @@ extern "C" int jt_head_bwd_tc(const float* dout, const float* feat, int ldf, con
 extern "C" int jt_sh_bwd_tc(const float* dout, const float* featdir, int ldf, const float* Wb, const int* n_dev,
                             int n_max, void* dcomps, int dcomps_bf16, void* stage, float* gWb, cudaStream_t stream) {
     JT_CHECK_ARG(dout && featdir && Wb && dcomps && stage && gWb && ldf >= 32 && ldf % 4 == 0);
-    JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
+    JT_CHECK_ARG(dcomps_bf16 == 1);                     // dcomps rows are bf16 [A][144] (what jt_vm_scatter_rays reads)
+    JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0 && (reinterpret_cast<uintptr_t>(dcomps) & 15) == 0);
     if (n_max <= 0) return JT_OK;
     long long tiles = ((long long)n_max + TM - 1) / TM;
     int grid_d = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
     int grid_w = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    if (int rc = set_smem(sh_bwd_data_kernel<false>, ShBwdSmem::total)) return rc;
-    if (int rc = set_smem(sh_bwd_data_kernel<true>, ShBwdSmem::total)) return rc;
+    if (int rc = set_smem(sh_bwd_data_kernel, ShBwdSmem::total)) return rc;
     if (int rc = set_smem(head_bwd_wgrad_kernel<3, 1, WG_SH_STAGES, WG_SH_STAGE_BYTES>, WG_SH_STAGES * WG_SH_STAGE_BYTES)) return rc;
     g_launches += 2;
     unsigned char* st = static_cast<unsigned char*>(stage);
-    if (dcomps_bf16)
-        sh_bwd_data_kernel<true><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
-    else
-        sh_bwd_data_kernel<false><<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max, dcomps, st);
+    sh_bwd_data_kernel<<<grid_d, NTB, ShBwdSmem::total, stream>>>(dout, featdir, ldf, Wb, n_dev, n_max,
+                                                                 static_cast<unsigned short*>(dcomps), st);
     head_bwd_wgrad_kernel<3, 1, WG_SH_STAGES, WG_SH_STAGE_BYTES><<<grid_w, TM, WG_SH_STAGES * WG_SH_STAGE_BYTES, stream>>>(
         st, n_dev, n_max, gWb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     JT_RETURN_LAUNCH();

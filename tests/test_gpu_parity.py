@@ -180,10 +180,12 @@ def test_midsize_against_oracle(blur, head):
         assert rel_err(p.grad.cpu(), params[k].grad) <= gtol, (k, rel_err(p.grad.cpu(), params[k].grad))
 
 
-@pytest.mark.parametrize("head", ["fp32", "tc"])
-def test_full_size_cfg2_properties(head):
-    """300^3 / 4096 rays / S=1000 (the benchmark workload): size-independent invariants."""
-    kw, run = jt.synth.config("cfg2")
+@pytest.mark.parametrize("head,wl", [("fp32", "cfg2"), ("tc", "cfg2"), ("tc", "cfg2_sh")])
+def test_full_size_cfg2_properties(head, wl):
+    """300^3 / 4096 rays / S=1000 (the benchmark workloads: SH shading = BASELINE configs[1], and the MLP_Fea
+    head on the same field): size-independent invariants."""
+    kw, run = jt.synth.config(wl)
+    shading = kw["shadingMode"]
     torch.manual_seed(0)
     m = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), DEV, **kw)
     m.head_precision = head
@@ -207,7 +209,7 @@ def test_full_size_cfg2_properties(head):
     assert 0.5 < v / (4096 * S) < 0.8
     # (2) render: weights + background transmittance partition unity; rgb in [0,1]
     og, dg = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
-    rgb, depth, acc = m.forward(default_opt(), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit)
+    rgb, depth, acc = m.forward(default_opt(shading), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit)
     assert bool(((rgb >= 0) & (rgb <= 1)).all()) and bool(((acc >= -1e-5) & (acc <= 1 + 1e-4)).all())
     assert torch.isfinite(depth).all()
     # (3) linearity of the backward pass in the upstream gradient
@@ -222,7 +224,7 @@ def test_full_size_cfg2_properties(head):
     sl = slice(100, 148)
     params = {k: v.detach().cpu().contiguous().clone() for k, v in m.state_dict().items()}
     field = vo.Field(aabb=m.aabb.cpu(), grid=[300] * 3, params=params, near_far=[2.0, 6.0], step_ratio=0.5,
-                     density_shift=-10.0, distance_scale=25.0, weight_thres=1e-6, act="softplus", shading="MLP_Fea")
+                     density_shift=-10.0, distance_scale=25.0, weight_thres=1e-6, act="softplus", shading=shading)
     oc = o[sl].cpu().clone().requires_grad_(True)
     rgb_ref, depth_ref, acc_ref = vo.render(field, oc, d[sl].cpu(), n_samples=S, white_bg=True,
                                             jitter=jit[sl].cpu().reshape(-1, 1))
@@ -230,7 +232,7 @@ def test_full_size_cfg2_properties(head):
     assert (rgb[sl].detach().cpu() - rgb_ref).abs().max() <= ABS_TOL
     assert (depth[sl].cpu() - depth_ref).abs().max() <= 2e-4
     og2 = o[sl].clone().requires_grad_(True)
-    rgb2 = m.forward(default_opt(), og2, d[sl], white_bg=True, is_train=True, N_samples=S, jitter=jit[sl])[0]
+    rgb2 = m.forward(default_opt(shading), og2, d[sl], white_bg=True, is_train=True, N_samples=S, jitter=jit[sl])[0]
     (rgb2 * w1[sl]).sum().backward()
     assert rel_err(og2.grad.cpu(), oc.grad) <= gtol
 
@@ -252,3 +254,33 @@ def test_empty_and_degenerate_batches():
     o37, d37 = g["rays_o"][:37].to(DEV), g["rays_d"][:37].to(DEV)
     r37 = m.forward(opt, o37, d37, white_bg=True, is_train=False, N_samples=g["n_samples"])[0]
     assert torch.allclose(r1, r37[:1], atol=1e-6)
+
+
+def test_empty_batches_on_the_sh_tensor_core_path():
+    """No valid sample / no appearance sample at all: the tcgen05 SH kernels must not be launched on garbage
+    (persistent grids read the counts from device memory) and the gradients are exact zeros."""
+    g = load_golden("sh_vm48")
+    m = module_from_golden(g, DEV)
+    m.head_precision = "tc"
+    opt = default_opt("SH")
+    o = torch.tensor([[10.0, 10.0, 10.0], [0.0, 0.0, 8.0], [9.0, 0.0, 0.0]], device=DEV)
+    d = torch.tensor([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]], device=DEV).requires_grad_(True)
+    rgb, depth, acc = m.forward(opt, o, d, white_bg=True, is_train=True, N_samples=g["n_samples"], bg_coin=False)
+    assert torch.equal(acc, torch.zeros_like(acc)) and torch.equal(rgb, torch.ones_like(rgb))
+    rgb.sum().backward()
+    assert torch.equal(d.grad, torch.zeros_like(d.grad))
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, torch.zeros_like(p.grad)), k
+    # strongly negative density feature everywhere (softplus -> 0): valid samples exist, but no weight passes
+    # the threshold -> A = 0
+    with torch.no_grad():
+        for i in range(3):
+            m.density_plane[i].abs_().add_(0.05)
+            m.density_line[i].fill_(-50.0)
+    o2, d2 = g["rays_o"][:40].to(DEV), g["rays_d"][:40].to(DEV).requires_grad_(True)
+    rgb, depth, acc = m.forward(opt, o2, d2, white_bg=True, is_train=True, N_samples=g["n_samples"], bg_coin=False)
+    assert int(jt.VMRender.last_counts[1].item()) == 0 and int(jt.VMRender.last_counts[0].item()) > 0
+    rgb.sum().backward()
+    assert torch.isfinite(d2.grad).all()
+    assert torch.equal(m.basis_mat.weight.grad, torch.zeros_like(m.basis_mat.weight.grad))

@@ -25,12 +25,23 @@
 
 namespace jt {
 
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2: two IEEE fp32 operations per instruction and per fma-pipe
+// slot). The walker is bound by instruction issue at ~2 warps per scheduler, and scalar FFMA occupies the fma
+// pipe for two cycles per warp: pairing the channel math halves both. A float4 is two aligned register pairs.
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat4(float2 l, float2 h) { return make_float4(l.x, l.y, h.x, h.y); }
+__device__ __forceinline__ float2 dup2(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float4 f4z() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-__device__ __forceinline__ void f4_fma(float4& acc, float4 a, float s) {
-    acc.x = fmaf(a.x, s, acc.x); acc.y = fmaf(a.y, s, acc.y); acc.z = fmaf(a.z, s, acc.z); acc.w = fmaf(a.w, s, acc.w);
+__device__ __forceinline__ void f4_fma(float4& acc, float4 a, float2 s) {          // acc += a * s
+    acc = cat4(__ffma2_rn(lo2(a), s, lo2(acc)), __ffma2_rn(hi2(a), s, hi2(acc)));
 }
-__device__ __forceinline__ float4 f4_mul2(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float f4_dot2(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 f4_mul2(float4 a, float4 b) { return cat4(__fmul2_rn(lo2(a), lo2(b)), __fmul2_rn(hi2(a), hi2(b))); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float2 s) { return cat4(__fmul2_rn(lo2(a), s), __fmul2_rn(hi2(a), s)); }
+__device__ __forceinline__ void f2_dot_acc(float2& acc, float4 a, float4 b) {      // acc += (a.xy*b.xy) + (a.zw*b.zw), lane-wise
+    acc = __ffma2_rn(lo2(a), lo2(b), acc);
+    acc = __ffma2_rn(hi2(a), hi2(b), acc);
+}
 __device__ __forceinline__ bool f4_any(float4 a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f; }
 
 // unclamped tap position on an axis of n texels (ATen grid_sampler, align_corners=True)
@@ -276,25 +287,26 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
         const float fx = pc.fx, fy = pc.fy, fl = pc.fl;
         const float wx0 = (1.f - fx) * mx0, wx1 = fx * mx1, wy0 = (1.f - fy) * my0, wy1 = fy * my1;
         const float wl0 = (1.f - fl) * ml0, wl1 = fl * ml1;
-        const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-        float dA = 0.f, dB = 0.f, dC = 0.f, dD = 0.f, dLa = 0.f, dLb = 0.f;      // sum_c gl*tap / gp*tap
+        const float2 w00 = dup2(wx0 * wy0), w10 = dup2(wx1 * wy0), w01 = dup2(wx0 * wy1), w11 = dup2(wx1 * wy1);
+        const float2 wl0p = dup2(wl0), wl1p = dup2(wl1);
+        float2 dA2 = dup2(0.f), dB2 = dup2(0.f), dC2 = dup2(0.f), dD2 = dup2(0.f), dLa2 = dup2(0.f), dLb2 = dup2(0.f);
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
             const float4 a = *pslot(pb, 0, k), b = *pslot(pb, 1, k), c = *pslot(pb, 2, k), d = *pslot(pb, 3, k);
             const float4 la = *lslot(lb, 0, k), lb4 = *lslot(lb, 1, k);
-            float4 pv, lv;
-            pv.x = a.x * w00 + b.x * w10 + c.x * w01 + d.x * w11; pv.y = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
-            pv.z = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11; pv.w = a.w * w00 + b.w * w10 + c.w * w01 + d.w * w11;
-            lv.x = la.x * wl0 + lb4.x * wl1; lv.y = la.y * wl0 + lb4.y * wl1;
-            lv.z = la.z * wl0 + lb4.z * wl1; lv.w = la.w * wl0 + lb4.w * wl1;
+            float4 pv = f4_scale(a, w00), lv = f4_scale(la, wl0p);
+            f4_fma(pv, b, w10); f4_fma(pv, c, w01); f4_fma(pv, d, w11);
+            f4_fma(lv, lb4, wl1p);
             const float4 g4 = gin_value(gc, k);
             const float4 gl = f4_mul2(g4, lv);       // dL/dP (interpolated plane value)
             const float4 gp = f4_mul2(g4, pv);       // dL/dL (interpolated line value)
             f4_fma(g00[k], gl, w00); f4_fma(g10[k], gl, w10); f4_fma(g01[k], gl, w01); f4_fma(g11[k], gl, w11);
-            f4_fma(gl0[k], gp, wl0); f4_fma(gl1[k], gp, wl1);
-            dA += f4_dot2(gl, a); dB += f4_dot2(gl, b); dC += f4_dot2(gl, c); dD += f4_dot2(gl, d);
-            dLa += f4_dot2(gp, la); dLb += f4_dot2(gp, lb4);
+            f4_fma(gl0[k], gp, wl0p); f4_fma(gl1[k], gp, wl1p);
+            f2_dot_acc(dA2, gl, a); f2_dot_acc(dB2, gl, b); f2_dot_acc(dC2, gl, c); f2_dot_acc(dD2, gl, d);
+            f2_dot_acc(dLa2, gp, la); f2_dot_acc(dLb2, gp, lb4);
         }
+        const float dA = dA2.x + dA2.y, dB = dB2.x + dB2.y, dC = dC2.x + dC2.y, dD = dD2.x + dD2.y;   // sum_c gl*tap
+        const float dLa = dLa2.x + dLa2.y, dLb = dLb2.x + dLb2.y;                                    // sum_c gp*tap
         // d/d index (ATen grid_sampler_2d_backward: out-of-range taps read as 0)
         const float dux = ((dB * mx1 - dA * mx0) * wy0 + (dD * mx1 - dC * mx0) * wy1) * sclx;
         const float duy = ((dC * my1 - dA * my0) * wx0 + (dD * my1 - dB * my0) * wx1) * scly;

@@ -396,13 +396,22 @@ def own_arm(args):
             evs.append((s, e))
         timed.host_ms = (time.perf_counter() - t_host) * 1e3 / k      # host time to ENQUEUE a step (launch-bound check)
         torch.cuda.synchronize()
+        timed.per_step = [round(s.elapsed_time(e), 3) for s, e in evs]
         return sum(s.elapsed_time(e) for s, e in evs)
 
+    tok = torch.zeros(1, device=dev)
+
     def barrier():
+        """Host barrier + device synchronize (the contract's bracket), then -- multi-GPU only -- a one-element
+        all-reduce left on the stream: a DEVICE-side rendezvous, so that the ranks' first timed step starts together
+        even though their hosts leave dist.barrier() a few ms apart (measured at N=8: the first timed step took
+        7.8 ms instead of 3.65 ms because rank 0 waited for the last host inside its first gradient all-reduce)."""
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(tok)
 
     for _ in range(max(args.warmup, 3)):
         step(pix_d, tgt_d)
@@ -413,7 +422,7 @@ def own_arm(args):
     l0 = jt._lib.launch_count()
     with ClockSampler(local) as clk:             # clocks are sampled across both timed regions
         ms = timed(lambda: step(pix_d, tgt_d), args.steps)
-        host_ms = timed.host_ms
+        host_ms, per_step = timed.host_ms, timed.per_step
         barrier()
         launches = jt._lib.launch_count() - l0
         ms_e2e = timed(step_e2e, args.steps)
@@ -623,6 +632,7 @@ def own_arm(args):
             "e2e": {"value": rays_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 3),
+            "step_ms_rank0": per_step,
             "clocks": clk.summary(),
         }
         if roof is not None:

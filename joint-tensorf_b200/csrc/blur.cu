@@ -96,8 +96,14 @@ struct BlurLaunch {
     float kraw[MAX_SETS][MAX_TAPS];  // adjoint only: taps in the original order (edge formulas)
 };
 
+// acc += k * x on packed fp32 pairs (sm_100 FFMA2: two IEEE fmas per instruction and per fma-pipe slot). The
+// 65-tap stencil is bound by fp32 FMA issue, not by HBM (2 x 65 FMAs per element against 8 bytes of traffic):
+// scalar FFMA caps the two plane passes at ~0.12 ms for the 17.3 M factor elements of cfg2, FFMA2 at half that.
 __device__ __forceinline__ void fma4(float4& a, const float k, const float4 x) {
-    a.x = fmaf(k, x.x, a.x); a.y = fmaf(k, x.y, a.y); a.z = fmaf(k, x.z, a.z); a.w = fmaf(k, x.w, a.w);
+    const float2 kk = make_float2(k, k);
+    const float2 lo = __ffma2_rn(kk, make_float2(x.x, x.y), make_float2(a.x, a.y));
+    const float2 hi = __ffma2_rn(kk, make_float2(x.z, x.w), make_float2(a.z, a.w));
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // 8 taps kk[0..7] applied to the window (lo = positions w..w+7, hi = w+8..w+15): acc[j] += kk[t] * x[w + j + t]

@@ -24,7 +24,7 @@ namespace jt {
 // APP == false: out[e] = sum_i sum_c P_ic * L_ic               (density feature)
 // APP == true : out[e][off_i + c] = P_ic * L_ic                (appearance components, before basis_mat)
 template <bool APP>
-__global__ void __launch_bounds__(256) vm_fwd_kernel(Factors F, const float4* __restrict__ samp,
+__global__ void __launch_bounds__(256, 4) vm_fwd_kernel(Factors F, const float4* __restrict__ samp,
                                                      const int* __restrict__ slot, const int* __restrict__ n_dev,
                                                      int n_fixed, float* __restrict__ out) {
     const int n = n_dev ? *n_dev : n_fixed;

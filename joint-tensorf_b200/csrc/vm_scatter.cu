@@ -104,7 +104,7 @@ struct StepPos {          // tap position of one sample on one plane/line pair
     int sid;              // ray * S + k
 };
 
-template <bool APP, int NQ, int I, bool GB16>
+template <bool APP, int NQ, int I, bool GB16, int THR = SC_THREADS>
 __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
                                            int& ray, int& ray_end, RaySums& rs, float4* __restrict__ sm) {
     const Factors& F = A.F;
@@ -118,8 +118,8 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
     const float sclx = 0.5f * (float)(W - 1), scly = 0.5f * (float)(H - 1), scll = 0.5f * (float)(L - 1);
     // this lane's staging slots (float4 index = slot * SC_THREADS): plane buffer b, tap c, quad k -> (b*4 + c)*NQ + k;
     // line buffer b, tap c, quad k -> 8 NQ + (b*2 + c)*NQ + k
-    auto pslot = [&](int b, int c, int k) -> float4* { return sm + ((b * 4 + c) * NQ + k) * SC_THREADS; };
-    auto lslot = [&](int b, int c, int k) -> float4* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * SC_THREADS; };
+    auto pslot = [&](int b, int c, int k) -> float4* { return sm + ((b * 4 + c) * NQ + k) * THR; };
+    auto lslot = [&](int b, int c, int k) -> float4* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * THR; };
 
     auto make_pos = [&](const float4 u4, const int sid) {
         const float u[3] = {u4.x, u4.y, u4.z};
@@ -407,9 +407,11 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
             return JT_ERR_LAUNCH;                                                                                   \
         vm_scatter_walk_kernel<APPV, NQV, MB, GB, LWV><<<grid, threads, smem, stream>>>(A, LW, wpc);                \
     }
+    // (64-thread CTAs with a 200-register cap -- five CTAs per SM instead of two -- spill and lose: 1.55 vs 1.22 ms;
+    // a minimum-blocks bound of 3 (168 registers) likewise: 2.28 ms.)
     if (app && gin_bf16) { if (nq == 3) JT_SC(true, 3, 2, true, 4) else if (nq == 2) JT_SC(true, 2, 3, true, 4) else JT_SC(true, 1, 3, true, 0) }
     else if (app) { if (nq == 3) JT_SC(true, 3, 2, false, 4) else if (nq == 2) JT_SC(true, 2, 3, false, 4) else JT_SC(true, 1, 3, false, 0) }
-    else { if (nq == 3) JT_SC(false, 3, 2, false, 4) else if (nq == 2) JT_SC(false, 2, 3, false, 4) else JT_SC(false, 1, 3, false, 0) }
+    else { if (nq == 3) JT_SC(false, 3, 2, false, 4) else if (nq == 2) JT_SC(false, 2, 3, false, 4) else JT_SC(false, 1, 4, false, 0) }
 #undef JT_SC
     JT_RETURN_LAUNCH();
 }

@@ -138,7 +138,8 @@ int jt_sh_shade(int bwd, const float* feat, int ldf, const int* aidx, const int*
 /* ---- K3, tensor-core path (tcgen05.mma + TMEM) ---------------------------- */
 /* Plumbing self test: mode 0  D[128][N] = A[128][K] * B[N][K]^T (K-major smem operands);
  * mode 1  D[m][n] = sum_s X[s][m] * Y[s][n] with X = A [128][Ma], Y = B [128][N]
- * (MN-major operands, the form the weight-gradient GEMMs use). bf16 products, fp32 sums. */
+ * (MN-major operands, the form the weight-gradient GEMMs use). bf16 products, fp32 sums.
+ * mode 2 = mode 0 with both operands stored as fp16. */
 int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, float* D, int K, int N, int Ma,
                    cudaStream_t stream);
 /* basis_mat (tensoRF.py:270) + positional_encoding (tensorBase.py:43-55) + MLPRender_Fea

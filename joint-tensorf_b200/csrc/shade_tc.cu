@@ -26,6 +26,7 @@ using namespace tc;
 // ------------------------------------------------------------------ self test of the MMA plumbing
 // mode 0: D[128][N] = A[128][K] * B[N][K]^T          (K-major operands)
 // mode 1: D[m][n]   = sum_s X[s][m] * Y[s][n]        (MN-major operands; X [128][Ma], Y [128][N], K = 128 rows)
+// mode 2: mode 0 with both operands stored as fp16
 __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float* __restrict__ A, int lda,
                                                           const float* __restrict__ B, int ldb, float* __restrict__ D,
                                                           int K, int N, int Ma) {
@@ -41,14 +42,24 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
         for (int c = 0; c < K / 8; ++c) {           // thread = row of A
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = A[(size_t)tid * lda + c * 8 + i];
-            store_chunk(ta, nullptr, 128, c, tid, v);
+            if (mode == 2) store_chunk_f16(ta, 128, c, tid, v); else store_chunk(ta, nullptr, 128, c, tid, v);
         }
-        stage_weight(tb, nullptr, B, ldb, N, K, N, K, nullptr, -1, 0);
+        if (mode == 2) {
+            for (int idx = tid; idx < N * (K / 8); idx += 128) {
+                const int chunk = idx / N, n = idx - chunk * N;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = B[(size_t)n * ldb + chunk * 8 + i];
+                store_chunk_f16(tb, N, chunk, n, v);
+            }
+        } else {
+            stage_weight(tb, nullptr, B, ldb, N, K, N, K, nullptr, -1, 0);
+        }
     } else {
         for (int c = 0; c < 128 / 8; ++c) {         // X tile padded to 128 columns with zeros
             float v[8];
@@ -70,6 +81,11 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(int mode, const float*
         tc_fence_after();
         if (mode == 0) {
             issue_gemm_kmajor<1>(tmem, ta, nullptr, tb, nullptr, K, N, N);
+        } else if (mode == 2) {
+            const uint32_t idesc = idesc_f16(128, N, 0, 0, 0, 0);
+            for (int ks = 0; ks < K / 16; ++ks)
+                mma_bf16(tmem, smem_desc(smem_u32(ta) + ks * 2 * 128 * 16, 128 * 16, 128),
+                         smem_desc(smem_u32(tb) + ks * 2 * N * 16, N * 16, 128), idesc, ks > 0);
         } else {
             const uint32_t idesc = idesc_bf16(128, N, 1, 1);
             for (int ks = 0; ks < 128 / 16; ++ks) {             // K = sample rows, 16 per step = 256 B
@@ -333,7 +349,7 @@ using namespace jt;
 
 extern "C" int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, float* D, int K, int N,
                               int Ma, cudaStream_t stream) {
-    JT_CHECK_ARG(A && B && D && (mode == 0 || mode == 1));
+    JT_CHECK_ARG(A && B && D && mode >= 0 && mode <= 2);
     JT_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 16 == 0 && K >= 16 && K <= 256 && Ma <= 128);
     const int smem = tile_bytes(128, 256) * 2;
     if (int rc = set_smem(tc_selftest_kernel, smem)) return rc;

@@ -11,6 +11,7 @@
 // writes 16 B per chunk, so a warp writes 512 contiguous bytes: conflict-free.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace jt {
@@ -113,6 +114,13 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// general kind::f16 descriptor: operand formats fp16 (0) or bf16 (1). Both operands must use the SAME format on
+// B200: a bf16 x fp16 product (tried for "bf16 gradients x fp16 activations" in the weight-gradient GEMMs) faults
+// at run time, so the staged tiles stay bf16 (jt_tc_selftest mode 2 covers fp16 x fp16).
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_bf16, int b_bf16) {
+    return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -130,6 +138,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // ---- bf16 packing ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
 // residual of the bf16 rounding (second term of the 2-term split a = hi + lo)
@@ -154,6 +166,13 @@ __device__ __forceinline__ void store_chunk(unsigned char* hi, unsigned char* lo
         h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]); h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
     }
     *reinterpret_cast<uint4*>(hi + (size_t)chunk * R * 16 + r * 16) = h;
+}
+
+// fp16 variant of store_chunk (single term: 11 significant bits, 8x finer than bf16)
+__device__ __forceinline__ void store_chunk_f16(unsigned char* t, int R, int chunk, int r, const float v[8]) {
+    uint4 h;
+    h.x = pack_f16(v[0], v[1]); h.y = pack_f16(v[2], v[3]); h.z = pack_f16(v[4], v[5]); h.w = pack_f16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(t + (size_t)chunk * R * 16 + r * 16) = h;
 }
 
 }  // namespace tc

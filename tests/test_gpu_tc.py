@@ -35,6 +35,18 @@ def test_umma_mnmajor(ma, n):
     assert float(d[ma:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("k,n", [(144, 32), (32, 16)])
+def test_umma_kmajor_fp16_operands(k, n):
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn(128, k, generator=g).to(DEV)
+    b = torch.randn(n, k, generator=g).to(DEV)
+    d = ops.tc_selftest(2, a, b, k, n)
+    ref = a.half().float() @ b.half().float().T
+    assert (d - ref).abs().max() <= 1e-5 * ref.abs().max() + 1e-5, float((d - ref).abs().max())
+    full = a @ b.T
+    assert (d - full).abs().max() <= 2e-3 * full.abs().max()
+
+
 def _head_inputs(a_count, seed=0):
     g = torch.Generator().manual_seed(seed)
     p = vo.init_params([8, 8, 8], [16] * 3, [48] * 3, 27, "MLP_Fea", 64, 2, 2, 0.1, 0.0, seed=seed)

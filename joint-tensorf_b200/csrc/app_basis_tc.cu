@@ -66,6 +66,10 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
     const uint32_t tmem = tmem_slot;
     uint32_t phase = 0;
     const int r = warp * 8 + grp;                 // tile row gathered by this lane quad
+    // Tuning notes (B200, cfg2: 0.62 ms): the kernel is latency-bound at 2 CTAs x 16 warps with exactly 64 registers --
+    // predicating half of the tap loads off changes its time by 2 % (not an LSU/L2 throughput problem), one CTA per
+    // SM with 128 registers is slower (0.82 ms), and fetching the next tile's slot / sample record / direction one
+    // tile ahead costs registers the tap loads need (0.82 - 0.91 ms).
 
     for (int tile = blockIdx.x; (long long)tile * TM < n; tile += gridDim.x) {
         const int row = tile * TM + r;

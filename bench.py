@@ -262,12 +262,14 @@ def algorithmic_bytes(name, V, A, cd, ca, ctot_a):
     return table.get(name)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-# this same workload (profiles/r01_ncu_full_v4.txt; cold caches, so an upper bound on a warm step)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of these
+# workloads (profiles/r01_ncu_full_v14.txt for the SH path and the gather / scatter kernels, r01_ncu_full_v4.txt for
+# the MLP_Fea head kernels; cold caches, so an upper bound on a warm step)
 NCU_DRAM_BYTES = {
-    "vm_app_bwd": 1.937981e9 + 0.328528e9, "vm_density_bwd": 0.089458e9 + 0.004454e9,
-    "vm_density_fwd": 0.053607e9 + 0.001437e9, "app_basis_fwd_tc": 0.453102e9 + 0.899889e9,
-    "head_mlp_fwd_tc": 0.299442e9 + 1.428690e9,
+    "vm_app_bwd": 1.923781e9 + 0.330893e9, "vm_density_bwd": 0.088398e9 + 0.003505e9,
+    "vm_density_fwd": 0.052985e9 + 0.001150e9, "app_basis_sh_fwd_tc": 0.580590e9 + 0.725284e9,
+    "sh_bwd_tc": 0.322786e9 + 0.724659e9 + 0.784006e9 + 0.003986e9,        # data kernel + basis weight-gradient kernel
+    "app_basis_fwd_tc": 0.453102e9 + 0.899889e9, "head_mlp_fwd_tc": 0.299442e9 + 1.428690e9,
     "head_bwd_tc": 0.906751e9 + 1.360633e9 + 2.863843e9 + 0.003652e9,      # data kernel + weight-gradient kernel
 }
 
@@ -460,7 +462,7 @@ def own_arm(args):
                     "ms_per_launch": per_launch_ms, "algorithmic_bytes": by,
                     "note": "algorithmic bytes count every tap as an HBM access (SURVEY 8d); the 69 MB of factors "
                             "stay in the 126 MB L2 and consecutive samples of a ray share cells, so frac > 1 and "
-                            "DRAM traffic << algorithmic bytes (profiles/r01_ncu_full_v4.txt)"}
+                            "DRAM traffic << algorithmic bytes (profiles/r01_ncu_full_v14.txt)"}
         elif fl is not None:
             ach = fl / (per_launch_ms * 1e-3) / 1e12
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",

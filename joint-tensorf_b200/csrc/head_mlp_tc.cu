@@ -25,8 +25,9 @@ template <int SPLIT, bool SAVE>
 struct HSmem {
     static constexpr int W1 = tile_bytes(H_, K1), W2 = tile_bytes(H_, K2);
     static constexpr int A1 = tile_bytes(TM, K1), A2 = tile_bytes(TM, K2);
-    static constexpr int off_w1 = 0, off_w2 = off_w1 + SPLIT * W1;
-    static constexpr int off_a1_hi = off_w2 + SPLIT * W2, off_a1_lo = off_a1_hi + A1;
+    static constexpr int NT = SPLIT == 2 ? 2 : 1;                      // operand terms kept in shared memory
+    static constexpr int off_w1 = 0, off_w2 = off_w1 + NT * W1;
+    static constexpr int off_a1_hi = off_w2 + NT * W2, off_a1_lo = off_a1_hi + A1;
     static constexpr int off_a2_hi = off_a1_lo + (SPLIT == 2 ? A1 : 0), off_a2_lo = off_a2_hi + A2;
     static constexpr int off_a3 = off_a2_lo + (SPLIT == 2 ? A2 : 0);
     static constexpr int off_w3 = off_a3 + (SAVE ? A2 : 0);            // fp32 [3][64] + b3[3]
@@ -69,8 +70,10 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
 
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_slot, 128);
-    stage_weight(w1_hi, w1_lo, W1, IN_, H_, IN_, H_, K1, b1, BIAS1, 1);
-    stage_weight(w2_hi, w2_lo, W2, H_, H_, H_, H_, K2, b2, H_, 0);
+    constexpr bool F16 = SPLIT == 3;
+    static_assert(!(F16 && SAVE), "the fp16 tiles are an inference-only format");
+    stage_weight<F16>(w1_hi, w1_lo, W1, IN_, H_, IN_, H_, K1, b1, BIAS1, 1);
+    stage_weight<F16>(w2_hi, w2_lo, W2, H_, H_, H_, H_, K2, b2, H_, 0);
     for (int i = tid; i < 3 * H_ + 3; i += HT) w3s[i] = i < 3 * H_ ? W3[i] : b3[i - 3 * H_];
     fence_async_smem();
     tc_fence_before();
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
             if (c >= ec0 && c < ec1) {
                 float v[8];
                 encode_chunk<true>(c, feat, dir, pm, v);
-                store_chunk(a1_hi, a1_lo, TM, c, r, v);
+                store_chunk_t<F16>(a1_hi, a1_lo, TM, c, r, v);
             }
         }
         fence_async_smem();
@@ -152,11 +155,11 @@ __global__ void __launch_bounds__(HT) head_mlp_fwd_kernel(const float* __restric
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(h[c * 8 + i], 0.f);
-                store_chunk(a2_hi, a2_lo, TM, hq * 2 + c, r, v);
+                store_chunk_t<F16>(a2_hi, a2_lo, TM, hq * 2 + c, r, v);
             }
             if (hq < 2) {
                 const float pad[8] = {hq == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                store_chunk(a2_hi, a2_lo, TM, 8 + hq, r, pad);
+                store_chunk_t<F16>(a2_hi, a2_lo, TM, 8 + hq, r, pad);
             }
         }
         fence_async_smem();
@@ -229,7 +232,8 @@ extern "C" int jt_head_mlp_fwd_tc(int split, const float* featdir, const float* 
                                   float fea_progress, float view_progress, float* rgb, void* stage,
                                   cudaStream_t stream) {
     JT_CHECK_ARG(featdir && W1 && b1 && W2 && b2 && W3 && b3 && rgb);
-    JT_CHECK_ARG(split == 1 || split == 2);
+    JT_CHECK_ARG(split >= 1 && split <= 3);
+    JT_CHECK_ARG(split != 3 || !stage);                  // fp16 operands: inference only (no staged tiles)
     JT_CHECK_ARG((reinterpret_cast<uintptr_t>(stage) & 127) == 0);
     if (n_max <= 0) return JT_OK;
     long long tiles = ((long long)n_max + TM - 1) / TM;
@@ -243,7 +247,8 @@ extern "C" int jt_head_mlp_fwd_tc(int split, const float* featdir, const float* 
         head_mlp_fwd_kernel<SP, SV><<<grid, HT, smem, stream>>>(featdir, W1, b1, W2, b2, W3, b3, n_dev, n_max,          \
                                                                 fea_progress, view_progress, rgb, st);                  \
     }
-    if (split == 1 && !st) JT_LAUNCH_H(1, false, 2)
+    if (split == 3) JT_LAUNCH_H(3, false, 1)      // 87 registers: one CTA per SM (capping at 64 for two spills: 0.59 vs 0.50 ms)
+    else if (split == 1 && !st) JT_LAUNCH_H(1, false, 2)
     else if (split == 1) JT_LAUNCH_H(1, true, 2)
     else if (!st) JT_LAUNCH_H(2, false, 1)
     else JT_LAUNCH_H(2, true, 1)

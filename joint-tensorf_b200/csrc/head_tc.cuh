@@ -31,6 +31,14 @@ __host__ __device__ constexpr int tile_bytes(int rows, int cols) { return rows *
 // ------------------------------------------------------------------ generic staging helpers
 // W (n, k) fp32 row-major [N][ldw] -> canonical bf16 tile of NR rows x KP cols. `kmap` selects the
 // source column of tile column k: 0 identity (k == bias_col takes bias[n]), 1 layer-1 tensor-core order.
+// F16: single-term fp16 tile (inference mode, see issue_gemm_kmajor) instead of bf16 hi (+ lo).
+template <bool F16>
+__device__ __forceinline__ void store_chunk_t(unsigned char* hi, unsigned char* lo, int R, int chunk, int r, const float v[8]) {
+    if (F16) store_chunk_f16(hi, R, chunk, r, v);
+    else store_chunk(hi, lo, R, chunk, r, v);
+}
+
+template <bool F16 = false>
 __device__ inline void stage_weight(unsigned char* hi, unsigned char* lo, const float* __restrict__ W, int ldw, int N, int K,
                              int NR, int KP, const float* __restrict__ bias, int bias_col, int kmap) {
     for (int idx = threadIdx.x; idx < NR * (KP / 8); idx += blockDim.x) {
@@ -48,18 +56,22 @@ __device__ inline void stage_weight(unsigned char* hi, unsigned char* lo, const 
             }
             v[i] = x;
         }
-        store_chunk(hi, lo, NR, chunk, n, v);
+        store_chunk_t<F16>(hi, lo, NR, chunk, n, v);
     }
 }
 
 // issue the k-steps of one GEMM: D[128 x N] = A[128 x K] * B[N x K]^T, both K-major tiles.
 // The descriptors of k-step ks differ from those of step 0 only in the start-address field
 // (+ 2 chunks), so they are one 64-bit add each: the issuing thread's chain stays short.
+// SPLIT = 1: bf16 operands; 2: hi + lo bf16 terms, 3 MMAs per product (fp32-class); 3: single-term fp16 operands
+// (11 significant bits, 8x finer than bf16: rgb within ~2e-5 of the fp32 head at a third of the MMAs and half the
+// shared memory -- used for inference only, because the backward's staged tiles must be bf16 for the range of the
+// gradients and a tcgen05 product cannot mix operand formats).
 template <int SPLIT>
 __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, const unsigned char* a_hi, const unsigned char* a_lo,
                                                   const unsigned char* b_hi, const unsigned char* b_lo, int K, int NR,
                                                   int N) {
-    const uint32_t idesc = idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc = SPLIT == 3 ? idesc_f16(128, N, 0, 0, 0, 0) : idesc_bf16(128, N, 0, 0);
     const uint32_t a_lbo = TM * 16, b_lbo = NR * 16;
     const uint64_t ah0 = smem_desc(smem_u32(a_hi), a_lbo, 128), bh0 = smem_desc(smem_u32(b_hi), b_lbo, 128);
     const uint64_t al0 = SPLIT == 2 ? smem_desc(smem_u32(a_lo), a_lbo, 128) : 0;

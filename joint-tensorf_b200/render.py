@@ -48,6 +48,8 @@ class RenderCfg:
         self.view_prog = 1.0
         self.head = "fp32"          # "fp32": SIMT GEMMs (strict parity) | "tc": tcgen05 fused head
         self.tc_fwd_split = 2       # 2: hi+lo bf16 operands (fp32-class forward), 1: plain bf16
+        self.grad_enabled = True    # torch.is_grad_enabled() at the call site (B200_VMSplit.forward sets it)
+        self.tc_infer_fp16 = True   # no-grad forward of the MLP_Fea head: single-term fp16 operands (rgb within ~2e-5)
         self.__dict__.update(kw)
 
 
@@ -190,7 +192,10 @@ class VMRender(torch.autograd.Function):
         if cfg.head == "tc":
             tc_supported(cfg, afs, raise_if_not=True)
             rgb = torch.empty((cap, 4), device=dev)
-            train = any(ctx.needs_input_grad)
+            # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), and grad mode is always
+            # off inside Function.forward: the caller records it in cfg.grad_enabled. Without this test every
+            # full-frame render ran the training forward (staging tiles written for a backward that never comes).
+            train = cfg.grad_enabled and any(ctx.needs_input_grad)
             feat = torch.empty((cap, 32), device=dev)             # feat 0..26 | 0 | view dir 28..30 | 0
             ws["stage"] = ops.head_tc_stage(cap, dev) if train else None
             if cfg.shading == "SH":
@@ -199,7 +204,10 @@ class VMRender(torch.autograd.Function):
             else:
                 ops.app_basis_fwd_tc(cfg.tc_fwd_split, afs, comp.samp, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w,
                                      a_count, cap, feat, ws["stage"])
-                ops.head_mlp_fwd_tc(cfg.tc_fwd_split, feat, *head, a_count, cap, cfg.fea_prog, cfg.view_prog, rgb,
+                # inference: fp16 operand tiles (one MMA per product, half the shared memory, two CTAs per SM); the
+                # training forward keeps the hi+lo bf16 split because its staged tiles feed the bf16 backward GEMMs
+                mlp_split = 3 if (not train and cfg.tc_infer_fp16 and cfg.tc_fwd_split == 2) else cfg.tc_fwd_split
+                ops.head_mlp_fwd_tc(mlp_split, feat, *head, a_count, cap, cfg.fea_prog, cfg.view_prog, rgb,
                                     ws["stage"])
         else:
             comps = torch.empty((cap, afs.ctot), device=dev)

@@ -537,6 +537,7 @@ class B200_VMSplit(torch.nn.Module):
             cfg.head = "tc"
 
         cfg.grad_sync = self.grad_sync
+        cfg.grad_enabled = torch.is_grad_enabled()
         dp, dl, ap, al = self._blurred_all(self.kernel_density, self.kernel_color)
         head = self.renderModule.head_params() if self.renderModule is not None else []
         return VMRender.apply(cfg, center.reshape(-1, 3), ray_dir.reshape(-1, 3), aux, *dp, *dl, *ap, *al,

@@ -45,5 +45,7 @@ for split in (1, 2):
         t = timeit(lambda: ops.app_basis_fwd_tc(split, afs, comp.samp, aidx, comp.sidx, d, S, False, wb, cnt, A, featdir, st))
         t2 = timeit(lambda: ops.head_mlp_fwd_tc(split, featdir, *head, cnt, A, 1.0, 1.0, rgb, st))
         print(f"split={split} save={save}: app_basis {t:.3f} ms   head_mlp {t2:.3f} ms")
+t3 = timeit(lambda: ops.head_mlp_fwd_tc(3, featdir, *head, cnt, A, 1.0, 1.0, rgb, None))
+print(f"split=3 (fp16 operand tiles, inference): head_mlp {t3:.3f} ms")
 comps = torch.zeros(A, 144, device=dev)
 print("vm_app_fwd (SIMT gather only):", timeit(lambda: ops.vm_gather_fwd(1, afs, comp.samp, aidx, cnt, A, comps)))

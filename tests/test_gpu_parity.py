@@ -178,6 +178,11 @@ def test_midsize_against_oracle(blur, head):
     assert rel_err(dg.grad.cpu(), dc.grad) <= gtol
     for k, p in m.named_parameters():
         assert rel_err(p.grad.cpu(), params[k].grad) <= gtol, (k, rel_err(p.grad.cpu(), params[k].grad))
+    # the no-grad call (fp16 operand tiles in the tensor-core MLP head) meets the same forward bound
+    with torch.no_grad():
+        rgb_inf, depth_inf, acc_inf = m.forward(default_opt(), o.to(DEV), d.to(DEV), **fkw)
+    assert (rgb_inf.cpu() - rgb_ref).abs().max() <= ABS_TOL
+    assert torch.equal(acc_inf, acc.detach())
 
 
 @pytest.mark.parametrize("head,wl", [("fp32", "cfg2"), ("tc", "cfg2"), ("tc", "cfg2_sh")])

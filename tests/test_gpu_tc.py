@@ -126,7 +126,7 @@ def test_head_bwd_tc_matches_fp32_autograd(a_count, dc_dtype):
         assert rel(gk, pr[k].grad) <= 2e-2, (k, rel(gk, pr[k].grad))
 
 
-@pytest.mark.parametrize("split,tol", [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize("split,tol", [(2, 3e-5), (1, 2e-2), (3, 1e-4)])
 @pytest.mark.parametrize("a_count", [1, 129, 5000])
 def test_app_basis_and_mlp_kernels_match_fp32(split, tol, a_count):
     """jt_app_basis_fwd_tc (gather + basis_mat on tensor cores) against the SIMT gather + fp32 matmul,
@@ -154,10 +154,12 @@ def test_app_basis_and_mlp_kernels_match_fp32(split, tol, a_count):
     feat_ref = comps[:a_count] @ d["basis_mat.weight"].T
     featdir = torch.full((cap, 32), 7.0, device=DEV)
     stage = ops.head_tc_stage(cap, DEV)
-    ops.app_basis_fwd_tc(split, fs, samp_d, aidx_d, sidx_d, rays_dd, S, False, d["basis_mat.weight"].contiguous(),
-                         cnt, cap, featdir, stage)
+    # split 3 (fp16 operand tiles) exists for the inference call of the MLP kernel only
+    ops.app_basis_fwd_tc(min(split, 2), fs, samp_d, aidx_d, sidx_d, rays_dd, S, False,
+                         d["basis_mat.weight"].contiguous(), cnt, cap, featdir, stage)
+    tol_b = 3e-5 if split == 3 else tol
     scale = max(1.0, float(feat_ref.abs().max()))
-    assert (featdir[:a_count, :27] - feat_ref).abs().max() <= tol * scale
+    assert (featdir[:a_count, :27] - feat_ref).abs().max() <= tol_b * scale
     dirs = rays_d[(sidx[aidx.long()] // S).long()]
     assert torch.equal(featdir[:a_count, 28:31].cpu(), dirs)
     assert float(featdir[a_count:].sub(7.0).abs().max()) == 0.0, "rows past the count must not be written"
@@ -169,7 +171,8 @@ def test_app_basis_and_mlp_kernels_match_fp32(split, tol, a_count):
     rgb = torch.zeros((cap, 4), device=DEV)
     names = ["renderModule.mlp.0.weight", "renderModule.mlp.0.bias", "renderModule.mlp.2.weight",
              "renderModule.mlp.2.bias", "renderModule.mlp.4.weight", "renderModule.mlp.4.bias"]
-    ops.head_mlp_fwd_tc(split, featdir, *[d[k].contiguous() for k in names], cnt, cap, 0.8, 0.6, rgb, stage)
+    ops.head_mlp_fwd_tc(split, featdir, *[d[k].contiguous() for k in names], cnt, cap, 0.8, 0.6, rgb,
+                        None if split == 3 else stage)
     field = vo.Field(aabb=torch.zeros(2, 3), grid=grid, params=p)
     ref = vo.shade_mlp_fea(field, dirs, featdir[:a_count, :27].cpu(), 0.6, 0.8)
     assert (rgb[:a_count, :3].cpu() - ref).abs().max() <= tol

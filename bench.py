@@ -47,7 +47,8 @@ def parse():
                     help="skip the second head variant of the 300^3 field (cfg2 <-> cfg2_sh) timed after the headline")
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--blur", type=float, default=0.0, help="c2f blur parameter (0 = off, cfg3 uses 0.15)")
-    ap.add_argument("--cpu-rays", type=int, default=512, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=2048,
+                    help="rays in the bounded CPU-baseline sample (2 timed fwd+bwd iterations: ~10-20 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the 800x800 full-frame inference timing")

@@ -34,14 +34,20 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
         const int b = off[r], e = off[r + 1];
         float carry = 1.0f, acc = 0.f, wz = 0.f;
         int cnt = 0;
+        // the inputs of the next 32 samples are requested before the current ones are scanned (one warp per ray:
+        // every exposed memory latency is paid ~18 times in a row)
+        float nsf = 0.f, ndj = 0.f, nz = 0.f;
+        if (b + lane < e) { nsf = sigfeat[b + lane]; ndj = dist[b + lane]; nz = samp[b + lane].w; }
         for (int j0 = b; j0 < e; j0 += 32) {
             const int j = j0 + lane;
+            const float csf = nsf, cdj = ndj, cz = nz;
+            if (j + 32 < e) { nsf = sigfeat[j + 32]; ndj = dist[j + 32]; nz = samp[j + 32].w; }
             float q = 1.0f, alpha = 0.f, z = 0.f;
             if (j < e) {
-                float sigma = density_act(sigfeat[j] + shift, act);
-                alpha = 1.0f - expf(-sigma * (dist[j] * dscale));
+                float sigma = density_act(csf + shift, act);
+                alpha = 1.0f - expf(-sigma * (cdj * dscale));
                 q = 1.0f - alpha + 1e-10f;
-                z = samp[j].w;
+                z = cz;
             }
             float p = q;                                     // inclusive product scan over the warp
 #pragma unroll
@@ -170,8 +176,10 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
             const int i = i0 + lane;                 // reverse index: j = e-1-i
             const int j = e - 1 - i;
             float dw = 0.f, w = 0.f;
-            if (i < len) {
+            float sf = 0.f, dj = 0.f, tj = 0.f;      // inputs of the second half, requested before the scan: the
+            if (i < len) {                           // kernel is one warp per ray and pays every exposed latency
                 w = weight[j];
+                sf = sigfeat[j]; dj = dist[j]; tj = trans[j];
                 dw = dacc;
                 const int a = app_of[j];
                 if (a >= 0) {
@@ -193,13 +201,13 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
             if (lane == 0) excl = 0.f;
             const float suffix = carry + excl;       // sum over samples behind j
             if (i < len) {
-                const float x = sigfeat[j] + shift;
+                const float x = sf + shift;
                 const float sigma = density_act(x, act);
-                const float dd = dist[j] * dscale;
+                const float dd = dj * dscale;
                 const float ex = expf(-sigma * dd);
                 const float alpha = 1.0f - ex;
                 const float q = 1.0f - alpha + 1e-10f;
-                const float dalpha = dw * trans[j] - suffix / q;
+                const float dalpha = dw * tj - suffix / q;
                 const float dsigma = dalpha * dd * ex;
                 dsig[j] = dsigma * density_act_grad(x, act);
                 dn += dalpha * sigma * ex * dd;      // d/d(norm) * norm

@@ -70,7 +70,8 @@ struct ScatterArgs {
     float* d_d;             // [N][3], accumulated
     float inv[3];           // 2 / aabbSize (normalize_coord)
     int S;                  // samples per ray (sidx decoding)
-    int seg;                // samples per walker segment
+    int seg;                // samples per walker segment (fixed), or
+    int seg_target;         // > 0: persistent grid, segment length chosen in the kernel (see vm_scatter_walk_kernel)
 };
 
 // One walker = LW lanes; lane `sub` owns the NQ channel quads sub, sub + LW, ... of a plane
@@ -341,11 +342,21 @@ __global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const
     const int qs = LW * 4;                               // channel stride between this lane's quads
     if (wl >= walkers_per_cta) return;
     float4* sm = sc_smem + threadIdx.x;
-    const int n_units = (n + A.seg - 1) / A.seg;
-    const int stride = gridDim.x * walkers_per_cta;
+    const int stride = gridDim.x * walkers_per_cta;      // walkers in the grid
+    // Segment length. The grid is persistent (one wave of resident CTAs) and the units are dealt round-robin, so the
+    // kernel takes ceil(units / walkers) rounds: a fixed length leaves up to a whole round idle at the end (measured
+    // on cfg2, fixed 32/48/64/80 samples: 1.11 / 1.02 / 1.05 / 0.97 ms). The count n is only known on the device,
+    // so every CTA derives the same length here: k = round(n / (walkers * target)) rounds of ceil(n / (k * walkers)).
+    int seg = A.seg;
+    if (A.seg_target > 0) {
+        const long long wt = (long long)stride * A.seg_target;
+        const long long k = max(1LL, ((long long)n + wt / 2) / wt);
+        seg = (int)max(1LL, ((long long)n + k * stride - 1) / (k * stride));
+    }
+    const int n_units = (n + seg - 1) / seg;
     for (int unit = blockIdx.x * walkers_per_cta + wl; unit < n_units; unit += stride) {
-        const int e0 = unit * A.seg;
-        const int e1 = min(e0 + A.seg, n);
+        const int e0 = unit * seg;
+        const int e1 = min(e0 + seg, n);
         int ray = -1, ray_end = INT_MIN;
         RaySums rs;
 #pragma unroll
@@ -383,7 +394,11 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     A.d_o = d_o; A.d_d = d_d;
     for (int a = 0; a < 3; ++a) A.inv[a] = h_inv[a];
     A.S = n_samples;
-    A.seg = 32;
+    // default: persistent grid, segment length derived in the kernel from the device-side count (target ~100
+    // samples). JT_SCATTER_SEG=<n> (tuning) restores fixed n-sample segments on a non-persistent grid.
+    static const int seg_env = getenv("JT_SCATTER_SEG") ? atoi(getenv("JT_SCATTER_SEG")) : 0;
+    A.seg = seg_env > 0 ? seg_env : 32;
+    A.seg_target = seg_env > 0 ? 0 : 100;
     // lanes per walker / quads per lane: 48 or 32 uniform channels -> 4 lanes x C/16 quads, anything else -> one
     // quad per lane. (One lane owning all 4 quads of a 16-channel plane has 2.4x fewer instructions but
     // un-coalesced taps: measured 0.77 ms vs 0.49 ms for the cfg2 density planes.)
@@ -395,7 +410,10 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     const int threads = ((wpc * LW + 31) / 32) * 32;
     long long units = ((long long)n_max + A.seg - 1) / A.seg;
     long long want = (units + wpc - 1) / wpc;
-    long long cap = max_ctas > 0 ? (long long)max_ctas : (long long)kNumSMs * 32;
+    const int resident = nq == 3 ? 2 : (nq == 2 || app) ? 3 : 4;   // CTAs per SM of the variant launched below (MINB)
+    long long cap = max_ctas > 0 ? (long long)max_ctas
+                                 : (A.seg_target > 0 ? (long long)kNumSMs * resident : (long long)kNumSMs * 32);
+    if (A.seg_target > 0) want = cap;                         // one resident wave; the kernel sizes the segments to fit
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
     const int smem = 12 * nq * SC_THREADS * 16;

@@ -100,6 +100,9 @@ int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_facto
  * The element list must be ray-major (as jt_march_compact / jt_alpha_fwd produce it).
  * d_o / d_d [N][3] must be initialised by the caller (zeros, or jt_ray_init for NDC rays).
  * gin_bf16 = 1 (app only): gin rows are bf16 [n][sum C] as jt_head_bwd_tc writes them.
+ * max_ctas = 0: persistent grid (one resident wave), segment length derived in the kernel from the device-side
+ * count; > 0: the same with at most max_ctas CTAs; < 0: fixed segments of -max_ctas samples on a non-persistent
+ * grid (leaves room for a collective running next to the kernel).
  * max_ctas > 0 caps the (persistent) grid, so that the kernel can share the SMs with another
  * kernel running on a second stream; 0 = fill the machine. */
 int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,

@@ -399,6 +399,11 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     static const int seg_env = getenv("JT_SCATTER_SEG") ? atoi(getenv("JT_SCATTER_SEG")) : 0;
     A.seg = seg_env > 0 ? seg_env : 32;
     A.seg_target = seg_env > 0 ? 0 : 100;
+    // max_ctas < 0: fixed segments of -max_ctas samples on a non-persistent grid. The fused render op asks for this
+    // for the density scatter of a data-parallel step: the NCCL all-reduce of the appearance gradients runs next to
+    // it and its CTAs can only get onto an SM when scatter CTAs retire (a persistent wave would hold every SM's
+    // registers until the end of the kernel and serialise the collective behind it).
+    if (max_ctas < 0) { A.seg = -max_ctas; A.seg_target = 0; max_ctas = 0; }
     // lanes per walker / quads per lane: 48 or 32 uniform channels -> 4 lanes x C/16 quads, anything else -> one
     // quad per lane. (One lane owning all 4 quads of a 16-channel plane has 2.4x fewer instructions but
     // un-coalesced taps: measured 0.77 ms vs 0.49 ms for the cfg2 density planes.)

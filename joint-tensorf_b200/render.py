@@ -301,8 +301,9 @@ class VMRender(torch.autograd.Function):
                             cfg.n_samples, cfg.h_inv, d_o, d_d)
         if sync is not None:
             sync.on_app_grads(flat[:n_app])          # 3/4 of the bytes: reduced while the density scatter runs
+        # data parallel: the appearance all-reduce runs next to this kernel -> non-persistent grid (80-sample segments)
         ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
-                            cfg.h_inv, d_o, d_d)
+                            cfg.h_inv, d_o, d_d, max_ctas=(-80 if sync is not None else 0))
         if sync is not None:
             # the current stream waits here for both reductions: whatever autograd does with the views next (hand
             # them to p.grad, clone them, feed the adjoint blur) sees the cross-rank sums

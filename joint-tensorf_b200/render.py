@@ -4,11 +4,15 @@ Sequence of C-ABI calls for one batch of rays (all on the current stream, no
 host synchronisation anywhere -- the reference syncs at every boolean-mask
 index):
 
-  forward   jt_march_compact -> jt_vm_gather_fwd(density) -> jt_alpha_fwd
-            -> jt_vm_gather_fwd(app) -> jt_gemm_nt(basis) -> shading head
+  forward   jt_march_compact -> jt_vm_gather_fwd(density) -> jt_alpha_fwd -> appearance + shading:
+              tcgen05, SH shading        jt_app_basis_sh_fwd_tc          (gather + basis_mat + SHRender, one kernel)
+              tcgen05, MLP_Fea head      jt_app_basis_fwd_tc -> jt_head_mlp_fwd_tc
+              strict fp32 (any head)     jt_vm_gather_fwd(app) -> jt_gemm_nt(basis) -> jt_pe_encode / jt_gemm_nt / jt_sh_shade
             -> jt_composite_fwd
-  backward  jt_render_bwd -> jt_ray_init -> jt_vm_scatter_rays(density) -> head backward
-            -> jt_vm_scatter_rays(app)      (pose-path gradients accumulate inside the scatters)
+  backward  jt_render_bwd -> jt_ray_init -> head backward (jt_sh_bwd_tc | jt_head_bwd_tc | fp32 GEMM chain)
+            -> jt_vm_scatter_rays(app) -> jt_vm_scatter_rays(density)
+            (pose-path gradients accumulate inside the scatters; with a gradient synchroniser attached the
+            appearance part of the flat gradient bucket is all-reduced while the density scatter runs)
 
 Sample counts (V valid samples, A appearance samples) stay on the device; the
 kernels read them from `ray_off[N]` / `app_off[N]` and run persistent grids.

@@ -186,3 +186,25 @@ def test_supervision_blur_taps_and_scales_match_oracle():
                 kref = (io.gaussian_kernel if o["blur_2d_mode"] == "uniform-gaussian" else io.average_kernel)(
                     wref, o["blur_2d_c2f_kernel_size"])
                 assert taps.shape == kref.shape and (taps - kref).abs().max() <= 1e-7, (name, it, sc)
+
+
+def test_llff_views_reproduce_the_ndc_ray_generator():
+    """synth.llff_views (pose / intrinsics matrices handed to the pose->ray kernel in bench.py's cfg4 leg) describes the
+    same cameras as synth.llff_ndc_rays (the closed-form generator used for the oracle-side LLFF rays)."""
+    import joint_tensorf_b200 as jt
+    pose, intr = jt.synth.llff_views(8, (756, 1008), seed=1)
+    assert pose.shape == (8, 3, 4) and intr.shape == (8, 3, 3)
+    rot = pose[:, :, :3]
+    eye = torch.eye(3).expand(8, 3, 3)
+    assert (rot @ rot.transpose(1, 2) - eye).abs().max() < 1e-5          # proper rotations
+    assert float(intr[0, 0, 0]) == pytest.approx(0.85 * 1008)
+    o, d, view = jt.synth.llff_ndc_rays(64, 8, (756, 1008), seed=1)
+    assert o.shape == (64, 3) and torch.isfinite(o).all() and torch.isfinite(d).all()
+    assert (o[:, 2] + 1.0).abs().max() < 1e-4                              # origins sit on the NDC near plane z = -1
+
+
+def test_workload_descriptions_name_the_baseline_config():
+    import joint_tensorf_b200 as jt
+    s = jt.synth.describe("cfg2_sh", 4096)
+    assert "300^3" in s and "3x16" in s and "3x48" in s and "app_dim 27" in s and "SH" in s and "4096 rays/GPU" in s
+    assert "MLP_Fea" in jt.synth.describe("cfg2") and "617x687x617" in jt.synth.describe("cfg4")

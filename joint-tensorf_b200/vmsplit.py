@@ -155,6 +155,9 @@ class B200_VMSplit(torch.nn.Module):
         # supported, else the fp32 SIMT head; "fp32" forces the strict-parity path; "tc" insists.
         self.head_precision = "auto"
         self.tc_fwd_split = 2
+        # no-grad calls (evaluation, full-frame rendering) of the tensor-core MLP_Fea head use single-term fp16
+        # operand tiles (rgb within ~2e-5 of the training forward, a quarter faster); False keeps them identical
+        self.tc_infer_fp16 = True
         self._reg_cache = None
         self.grad_sync = None      # parallel.OverlappedGradSync when training data-parallel
         self.reset(aabb, gridSize, density_n_comp, appearance_n_comp, app_dim, density_shift, alphaMask_thres,
@@ -530,7 +533,8 @@ class B200_VMSplit(torch.nn.Module):
             distance_scale=float(self.distance_scale), thres=float(self.rayMarch_weight_thres),
             depth_bias=-float(self.near_far[0]) + 0.05, shading=self.shadingMode, app_dim=int(self.app_dim),
             fea_pe=int(self.fea_pe), view_pe=int(self.view_pe), hidden=int(self.featureC),
-            fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress), tc_fwd_split=int(self.tc_fwd_split))
+            fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress), tc_fwd_split=int(self.tc_fwd_split),
+            tc_infer_fp16=bool(self.tc_infer_fp16))
         from .render import tc_supported
         if self.head_precision == "tc" or (self.head_precision == "auto" and tc_supported(cfg) and
                                            sum(self.app_n_comp) == 144):

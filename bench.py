@@ -32,6 +32,7 @@ import torch  # noqa: E402
 
 METRIC = "rays/sec fwd+bwd (300^3 VM, 4096-ray batch)"
 UNIT = "rays/s"
+RENDER_METRIC = "ms per 800x800 frame (300^3 VM field, image-sharded full-frame inference)"
 
 
 def parse():
@@ -47,8 +48,15 @@ def parse():
                     help="skip the second head variant of the 300^3 field (cfg2 <-> cfg2_sh) timed after the headline")
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--blur", type=float, default=0.0, help="c2f blur parameter (0 = off, cfg3 uses 0.15)")
-    ap.add_argument("--cpu-rays", type=int, default=2048,
-                    help="rays in the bounded CPU-baseline sample (2 timed fwd+bwd iterations: ~10-20 s of host work)")
+    ap.add_argument("--cpu-rays", type=int, default=0,
+                    help="rays per step of the CPU reference / cpu_baseline legs (0 = the full --rays batch)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --rays per GPU, strong = --rays in total, sharded over the ranks (SURVEY 8e)")
+    ap.add_argument("--mode", default="train", choices=["train", "render"],
+                    help="render = BASELINE configs[4]: --frames full 800x800 frames, image-sharded over the ranks, ms/frame")
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"],
+                    help="VM factor storage the gathers read (fp32 master parameters either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-render", action="store_true", help="skip the 800x800 full-frame inference timing")
@@ -219,60 +227,196 @@ def time_aten_gpu(workload, n_rays, steps, warmup, dev):
     return n_rays / sec, sec
 
 
+def cfg_head(model):
+    """"tc" when the module will pick the tcgen05 head for its configuration, else "fp32"."""
+    hp = model.head_precision
+    if hp == "fp32":
+        return "fp32"
+    return "tc" if (hp == "tc" or model.tc_available()) else "fp32"
+
+
 def synth_describe(workload, n_rays=None):
     from joint_tensorf_b200 import synth
     return synth.describe(workload, n_rays)
+
+
+def time_cpu_reference(workload, n_rays, steps, warmup, blur, budget_s=240.0):
+    """The reference on the host cores: the UNMODIFIED `BAT_VMSplit` when its files are present (/root/reference in
+    the build container, the staged oracle/_ref on the GPU box: kind "reference"), else the oracle restatement
+    (kind "port"). Returns a dict with rays/s, seconds per step, cores, steps done and the kind."""
+    from oracle import reference_arm as ra
+    if ra.root() is not None:
+        rps, sec, cores, done, warm = ra.time_reference(workload, n_rays, steps, warmup, blur, budget_s)
+        return dict(rps=rps, sec=sec, cores=cores, steps=done, warmup=warm, kind="reference",
+                    what="unmodified reference BAT_VMSplit.forward + backward (model/tensorf_repr/batBase.py:44-165), "
+                         f"torch CPU, {cores} threads" +
+                         ("; SHRender called through a 5->3 argument wrapper (the reference's own call site "
+                          "crashes, SURVEY B-1)" if workload.endswith("_sh") else ""))
+    rps, sec, cores = time_cpu_port(workload, n_rays, steps, warmup, blur)
+    return dict(rps=rps, sec=sec, cores=cores, steps=steps, warmup=warmup, kind="port",
+                what=f"oracle/vm_oracle.py restatement (same ATen CPU operators as the reference), {cores} threads")
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_rays
-    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
-    rps, sec, cores = time_cpu_port(args.workload, n, steps, warm, args.blur)
+    if args.mode == "render":
+        return reference_render_arm(args)
+    n = args.cpu_rays or args.rays
+    # every step is the full ray batch (~8 s on 16 threads at cfg2_sh): the run stops early when 4 minutes are spent
+    r = time_cpu_reference(args.workload, n, max(1, args.steps), max(0, args.warmup), args.blur, budget_s=240.0)
+    rps = r["rps"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": synth_describe(args.workload) + f", {n}-ray sample of the {args.rays}-ray batch, fwd+bwd",
-                   "blur": args.blur},
-        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} of 4096 rays per step, {steps} steps, oracle/vm_oracle.py (torch CPU, "
-                                   f"{cores} threads)"},
+        "impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": r["sec"] * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": synth_describe(args.workload) + f", {n}-ray batch, fwd+bwd", "blur": args.blur,
+                   "note": "rays resident, no pose generation, optimizer step excluded; steps stop at a 240 s budget"},
+        "cpu_baseline": {"value": rps, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{n} rays per step (the full batch), {r['steps']} timed steps after {r['warmup']} "
+                                   f"warm-up: {r['what']}"},
         "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def reference_render_arm(args):
+    """configs[4] on the host cores: a bounded sample (16384 rays of one 800x800 frame, no-grad forward of the
+    unmodified reference / the port), extrapolated to ms per full frame and labelled as such."""
+    from joint_tensorf_b200 import synth
+    from oracle import reference_arm as ra
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 16384
+    o, d = synth.frame_rays(0)
+    sel = torch.randperm(o.shape[0], generator=torch.Generator().manual_seed(0))[:n]
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    kw, run = synth.config(args.workload)
+    kind = "reference" if ra.root() is not None else "port"
+    if kind == "reference":
+        import contextlib
+        import io
+        m, opt, run = ra.build_field(args.workload)
+
+        def fwd():
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                return m.forward(opt, o, d, white_bg=run["white_bg"], is_train=False, ndc_ray=run["ndc"],
+                                 N_samples=run["n_samples"])[0]
+    else:
+        from oracle import vm_oracle as vo
+        field, run = oracle_field(args.workload)
+
+        def fwd():
+            with torch.no_grad():
+                return vo.render(field, o, d, n_samples=run["n_samples"], white_bg=run["white_bg"], ndc=run["ndc"])[0]
+    fwd()
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        fwd()
+    sec = (time.perf_counter() - t0) / reps
+    ms_frame = sec * (800 * 800 / n) * 1e3
+    line = {"impl": "reference", "metric": RENDER_METRIC, "value": ms_frame, "unit": "ms/frame", "n_gpus": args.gpus,
+            "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": synth_describe(args.workload) + ", 800x800 full-frame inference",
+                       "note": f"EXTRAPOLATED from {n} rays of one frame (a full frame is ~20 min of host time)"},
+            "cpu_baseline": {"value": ms_frame, "unit": "ms/frame", "cores": cores, "kind": kind,
+                             "sample": f"{n} of 640000 rays, {reps} timed no-grad forwards, extrapolated x{800 * 800 / n:.1f}"},
+            "e2e": {"value": ms_frame, "unit": "ms/frame", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------- own arm
-def algorithmic_bytes(name, V, A, cd, ca, ctot_a):
-    """bytes a kernel must move per launch (fp32 factors)."""
+def logical_bytes(name, V, A, cd, ca, ctot_a):
+    """SURVEY.md section 8(d)'s LOGICAL figure: every tap counted as an HBM access (fp32 factors). Kept for
+    reference only -- the factors live in L2 and cells are shared along a ray, so this is not a roofline."""
     s = 4
-    dens_f = V * (18 * cd * s + 16)                 # 3 x (4+2) taps x C_d x 4 B + coords in + feature out
-    app_f = A * (18 * ca * s + 12 + 4 * ctot_a)     # taps + coords + component row out (un-fused)
-    app_fused = A * (18 * ca * s + 12)              # taps + coords; the component row stays on chip
+    dens_f = V * (18 * cd * s + 16)
+    app_fused = A * (18 * ca * s + 12)
     table = {
-        "vm_density_fwd": dens_f,
-        "vm_app_fwd": app_f,
-        "app_basis_fwd_tc": app_fused + A * 128,    # + feat/dir row out
-        "app_basis_sh_fwd_tc": app_fused + A * 32,  # + rgb and view direction out
-        "vm_density_bwd": V * (3 * 18 * cd * s + 4 + 16),
-        "vm_app_bwd": A * (3 * 18 * ca * s + 4 * ctot_a + 16),
+        "vm_density_fwd": dens_f, "vm_app_fwd": A * (18 * ca * s + 12 + 4 * ctot_a),
+        "app_basis_fwd_tc": app_fused + A * 128, "app_basis_sh_fwd_tc": app_fused + A * 32,
+        "vm_density_bwd": V * (3 * 18 * cd * s + 4 + 16), "vm_app_bwd": A * (3 * 18 * ca * s + 4 * ctot_a + 16),
     }
     return table.get(name)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of these
-# workloads (profiles/r01_ncu_full_v14.txt for the SH path and the gather / scatter kernels, r01_ncu_full_v4.txt for
-# the MLP_Fea head kernels; cold caches, so an upper bound on a warm step)
-NCU_DRAM_BYTES = {
-    "vm_app_bwd": 1.923781e9 + 0.330893e9, "vm_density_bwd": 0.088398e9 + 0.003505e9,
-    "vm_density_fwd": 0.052985e9 + 0.001150e9, "app_basis_sh_fwd_tc": 0.580590e9 + 0.725284e9,
-    "sh_bwd_tc": 0.322786e9 + 0.724659e9 + 0.784006e9 + 0.003986e9,        # data kernel + basis weight-gradient kernel
-    "app_basis_fwd_tc": 0.453102e9 + 0.899889e9, "head_mlp_fwd_tc": 0.299442e9 + 1.428690e9,
-    "head_bwd_tc": 0.906751e9 + 1.360633e9 + 2.863843e9 + 0.003652e9,      # data kernel + weight-gradient kernel
+def compulsory_bytes(name, V, A, fbytes_d, fbytes_a, gbytes_d, gbytes_a, ctot_a, gin_bytes, train=True):
+    """HBM bytes the IMPLEMENTATION's data flow cannot avoid, per launch: the per-sample streams
+    (sample records 16 B + index 4 B (+ appearance slot 4 B), upstream gradients, staged operand tiles), ONE read of
+    the factor set the kernel gathers from (fbytes_*: its bytes as stored, fp32 or bf16) and ONE write-back of the
+    gradient planes it reduces into (gbytes_*, fp32; the REDs resolve in L2). Everything a kernel moves beyond this
+    (`traffic` from ncu) is re-reads caused by L2 overflow."""
+    rec_v, rec_a = 16 + 4, 16 + 4 + 4
+    table = {
+        "vm_density_fwd": V * (rec_v + 4) + fbytes_d,
+        "vm_density_bwd": V * (rec_v + 4) + fbytes_d + gbytes_d,
+        "vm_app_fwd": A * (rec_a + 4 * ctot_a) + fbytes_a,
+        "vm_app_bwd": A * (rec_a + gin_bytes * ctot_a) + fbytes_a + gbytes_a,
+        # gather + basis_mat (+ SHRender): records in, rgb + view direction (SH) or the 128-byte feat/dir row out,
+        # + the bf16 component tile staged for the basis_mat weight gradient when training
+        "app_basis_sh_fwd_tc": A * (rec_a + 32 + (2 * ctot_a if train else 0)) + fbytes_a,
+        "app_basis_fwd_tc": A * (rec_a + 128 + (2 * ctot_a if train else 0)) + fbytes_a,
+        # SH backward: dpre + direction in, bf16 dcomps + the DF tile out; weight-gradient kernel reads both tiles
+        "sh_bwd_tc": A * (32 + 2 * ctot_a + 64) + A * (2 * ctot_a + 64),
+        "head_mlp_fwd_tc": A * (128 + 16 + (320 + 160 + 160 if train else 0)),
+        # data kernel: dout + feat row + the relu-mask halves of A2 / A3 in, D2 / D1 / DF / DO tiles + dcomps out;
+        # weight-gradient kernel: all eight staged tiles (1264 B per sample, head_tc.cuh) in
+        "head_bwd_tc": A * (16 + 128 + 256 + 336 + gin_bytes * ctot_a + 1264),
+        "alpha_fwd": V * (4 + 4 + 16 + 8 + 8), "render_bwd": V * (4 + 4 + 8 + 4 + 16 + 16 + 4),
+        "composite_fwd": A * (4 + 4 + 16),
+    }
+    return table.get(name)
+
+
+def l1_fill_bytes(name, V, A, cd, ca, s_d, s_a):
+    """The binding unit of the gather / scatter kernels is not HBM but the SM's L1 data pipe (ncu:
+    l1tex__data_pipe_lsu_wavefronts 66-71 % of peak on these kernels, 128 B per clock per SM): bytes that must cross
+    it per launch in the current design = every tap of every sample delivered to registers once (fp32 or bf16 as
+    stored) (+ the same volume again as REDs and staging copies in the scatter, not counted here)."""
+    table = {
+        "vm_density_fwd": V * 18 * cd * s_d, "vm_density_bwd": V * 18 * cd * s_d,
+        "vm_app_fwd": A * 18 * ca * s_a, "app_basis_fwd_tc": A * 18 * ca * s_a, "app_basis_sh_fwd_tc": A * 18 * ca * s_a,
+        "vm_app_bwd": A * 18 * ca * s_a,
+    }
+    return table.get(name)
+
+
+# timer span (ops.TIMER) -> the kernel functions launched inside it, for the ncu look-up
+SPAN_KERNELS = {
+    "vm_app_bwd": ["vm_scatter_walk_kernel<1"], "vm_density_bwd": ["vm_scatter_walk_kernel<0"],
+    "vm_density_fwd": ["vm_fwd_kernel<0"], "vm_app_fwd": ["vm_fwd_kernel<1"],
+    "app_basis_sh_fwd_tc": ["app_basis_fwd_kernel"], "app_basis_fwd_tc": ["app_basis_fwd_kernel"],
+    "sh_bwd_tc": ["sh_bwd_data_kernel", "head_bwd_wgrad_kernel"], "head_mlp_fwd_tc": ["head_mlp_fwd_kernel"],
+    "head_bwd_tc": ["head_bwd_data_kernel", "head_bwd_wgrad_kernel"], "alpha_fwd": ["alpha_fwd_kernel"],
+    "render_bwd": ["render_bwd_kernel"], "composite_fwd": ["composite_fwd_kernel"],
 }
+
+
+def ncu_lookup(span, workload, storage):
+    """dram bytes (read + write) and L1 data-pipe utilisation of the kernels of `span` from the committed
+    `ncu --set full` capture of THIS workload (profiles/ncu_kernels.json, written by scripts/ncu_summary.py --json
+    from the .ncu-rep of the same code; its `commit` field says which). None when no capture matches."""
+    try:
+        db = json.load(open(os.path.join(ROOT, "profiles", "ncu_kernels.json")))
+    except Exception:
+        return None
+    cap = db.get(f"{workload}:{storage}")
+    if not cap:
+        return None
+    tot, l1, found = 0.0, [], []
+    for pat in SPAN_KERNELS.get(span, []):
+        hit = [k for k in cap["kernels"] if k["name"].replace("void ", "").startswith(pat)]
+        if not hit:
+            return None
+        k = hit[0]
+        tot += k["dram_read"] + k["dram_write"]
+        l1.append(k.get("l1_lsu_wavefront_pct"))
+        found.append(k["name"][:60])
+    return {"traffic": tot, "l1_data_pipe_pct_ncu": l1[0] if l1 else None, "kernels": found,
+            "capture": cap.get("file"), "commit": cap.get("commit")}
 
 
 def gemm_flops(name, A, F, ctot, in_dim, H):
@@ -318,8 +462,10 @@ def own_arm(args):
     model = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), dev, **kw)
     from joint_tensorf_b200.options import default_opt
     model.head_precision = args.head
+    model.factor_storage = args.storage
     opt = default_opt(model.shadingMode, run["ndc"])
-    N, S = args.rays, run["n_samples"]
+    # weak scaling: --rays per GPU; strong scaling: --rays in total, a contiguous 1/world slice per rank
+    N, S = (args.rays // world if args.scaling == "strong" else args.rays), run["n_samples"]
     # Pose side of the step (SURVEY 8d protocol): 32 hemisphere views, pose noise N(0, 0.15^2) composed into the
     # fixed pose (bat.py:34,346-348), se3_refine = 0 and trainable (bat.py:350), 128 pixels shared by all views
     # (nerf.py:657-658) -> N = 4096 rays generated by jt_pose_rays_fwd, gradients back to se3_refine.
@@ -455,34 +601,64 @@ def own_arm(args):
         ops.TIMER.enabled = False
         V, A = (int(t.item()) for t in jt.VMRender.last_counts)      # measured on the last step's batch
         breakdown = {k: round(v[0] / reps, 4) for k, v in sorted(summ.items(), key=lambda kv: -kv[1][0])}
-        top = next(iter(breakdown))
         cd, ca = model.density_n_comp[0], model.app_n_comp[0]
+        ctot_a = sum(model.app_n_comp)
         F_, H_ = model.app_dim, model.featureC
         in_dim = F_ + 3 + 2 * model.fea_pe * F_ + 6 * model.view_pe
-        per_launch_ms = summ[top][0] / summ[top][1]
-        by = algorithmic_bytes(top, V, A, cd, ca, sum(model.app_n_comp))
-        fl = gemm_flops(top, A, F_, sum(model.app_n_comp), in_dim, H_)
-        if by is not None:
-            ach = by / (per_launch_ms * 1e-3) / 1e9
-            roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": NCU_DRAM_BYTES.get(top), "peak_source": peak_src,
-                    "ms_per_launch": per_launch_ms, "algorithmic_bytes": by,
-                    "note": "algorithmic bytes count every tap as an HBM access (SURVEY 8d); the 69 MB of factors "
-                            "stay in the 126 MB L2 and consecutive samples of a ray share cells, so frac > 1 and "
-                            "DRAM traffic << algorithmic bytes (profiles/r01_ncu_full_v14.txt)"}
-        elif fl is not None:
-            ach = fl / (per_launch_ms * 1e-3) / 1e12
-            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": NCU_DRAM_BYTES.get(top), "peak_source": peak_src,
-                    "ms_per_launch": per_launch_ms}
-        gk = [k for k in ("vm_density_fwd", "vm_app_fwd", "app_basis_fwd_tc", "app_basis_sh_fwd_tc", "vm_density_bwd",
-                          "vm_app_bwd") if k in breakdown]
-        gather = sum(breakdown[k] for k in gk)
-        gbytes = sum(algorithmic_bytes(k, V, A, cd, ca, sum(model.app_n_comp)) for k in gk)
-        if roof is not None and gather > 0:
-            roof["vm_gather_fwd_bwd"] = {"ms": gather, "achieved": gbytes / (gather * 1e-3) / 1e9,
-                                         "frac": gbytes / (gather * 1e-3) / 1e9 / hbm_peak, "V": V, "A": A,
-                                         "kernels": gk}
+        s_el = 2 if args.storage == "bf16" else 4
+        n_d = sum(p.numel() for p in [*model.density_plane, *model.density_line])
+        n_a = sum(p.numel() for p in [*model.app_plane, *model.app_line])
+        gin_b = 2 if cfg_head(model) == "tc" else 4
+        sm_clock = 1.965e9
+        l1_peak = 148 * 128 * sm_clock / 1e9          # GB/s: one 128-byte L1 data-pipe wavefront per clock per SM
+
+        def roof_of(name):
+            per_ms = summ[name][0] / summ[name][1]
+            cb = compulsory_bytes(name, V, A, n_d * s_el, n_a * s_el, n_d * 4, n_a * 4, ctot_a, gin_b)
+            fl = gemm_flops(name, A, F_, ctot_a, in_dim, H_)
+            ncu = ncu_lookup(name, args.workload, args.storage)
+            if cb is None:
+                return None
+            ach = cb / (per_ms * 1e-3) / 1e9
+            r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                 "traffic": ncu["traffic"] if ncu else None, "peak_source": peak_src, "ms_per_launch": per_ms,
+                 "algorithmic_bytes": cb,
+                 "algorithmic_bytes_what": "compulsory HBM bytes of the data flow: per-sample streams + one read of the "
+                                           "factors + one write-back of the gradient planes (bench.py compulsory_bytes)",
+                 "logical_bytes_survey_8d": logical_bytes(name, V, A, cd, ca, ctot_a)}
+            if ncu:
+                r["traffic_over_algorithmic"] = ncu["traffic"] / cb
+                r["ncu"] = {k: ncu[k] for k in ("kernels", "capture", "commit")}
+            lb = l1_fill_bytes(name, V, A, cd, ca, s_el, s_el)
+            if lb is not None:
+                r["binding_unit"] = {"unit": "L1 data pipe (LSU wavefronts, 128 B/clk/SM x 148 SMs at 1965 MHz)",
+                                     "bytes": lb, "achieved": lb / (per_ms * 1e-3) / 1e9, "peak": l1_peak,
+                                     "frac": lb / (per_ms * 1e-3) / 1e9 / l1_peak,
+                                     "ncu_l1_data_pipe_pct": ncu["l1_data_pipe_pct_ncu"] if ncu else None,
+                                     "what": "tap bytes delivered to registers once per sample (fp32 or bf16 as stored)"}
+            if fl is not None:
+                r["tensor"] = {"achieved": fl / (per_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                               "frac": fl / (per_ms * 1e-3) / 1e12 / tf_peak}
+            return r
+
+        top = next((k for k in breakdown if compulsory_bytes(k, V, A, 1, 1, 1, 1, ctot_a, gin_b) is not None), None)
+        roof = roof_of(top) if top else None
+        if roof is not None:
+            roof["V"], roof["A"] = V, A
+            # the north star's named targets: gather, composite (and blur when active) kernels against HBM
+            fam = {}
+            for k in breakdown:
+                if k != top and compulsory_bytes(k, V, A, 1, 1, 1, 1, ctot_a, gin_b) is not None:
+                    rk = roof_of(k)
+                    fam[k] = {"ms": rk["ms_per_launch"], "hbm_frac": round(rk["frac"], 4),
+                              "traffic": rk["traffic"], "algorithmic_bytes": rk["algorithmic_bytes"],
+                              "l1_frac": round(rk["binding_unit"]["frac"], 4) if "binding_unit" in rk else None}
+            roof["other_kernels"] = fam
+            step_bytes = sum(compulsory_bytes(k, V, A, n_d * s_el, n_a * s_el, n_d * 4, n_a * 4, ctot_a, gin_b) or 0
+                             for k in breakdown)
+            roof["step"] = {"compulsory_bytes": step_bytes, "ms_at_hbm_peak": step_bytes / hbm_peak / 1e6,
+                            "ms_measured": ms / args.steps,
+                            "hbm_frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak}
 
     # second half of BASELINE.json's metric: one 800x800 frame (640 000 rays, cfg2 field, is_train=False, no
     # blur) rendered like the reference's render_by_slices (model/nerf.py:728-740), rays resident on the device
@@ -528,6 +704,7 @@ def own_arm(args):
         torch.manual_seed(0)
         model_o = jt.B200_VMSplit(torch.tensor(kw_o.pop("aabb")), kw_o.pop("gridSize"), dev, **kw_o)
         model_o.head_precision = args.head
+        model_o.factor_storage = args.storage
         opt_o = default_opt(model_o.shadingMode, run["ndc"])
         step_o = make_step(model_o, opt_o, [p for p in model_o.parameters()] + [se3_refine])
         for _ in range(max(args.warmup, 3)):
@@ -604,10 +781,11 @@ def own_arm(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, sec, cores = time_cpu_port(args.workload, args.cpu_rays, 2, 1, args.blur)
-        cpu = {"value": rps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_rays} of {N} rays, 2 timed fwd+bwd iterations of oracle/vm_oracle.py "
-                         f"(torch CPU, {cores} threads)"}
+        n_cpu = args.cpu_rays or N
+        r = time_cpu_reference(args.workload, n_cpu, 2, 1, args.blur, budget_s=60.0)
+        cpu = {"value": r["rps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{n_cpu} of {N} rays per step, {r['steps']} timed fwd+bwd steps after {r['warmup']} warm-up: "
+                         f"{r['what']}"}
 
     aten = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -626,13 +804,15 @@ def own_arm(args):
         line = {
             "metric": METRIC, "value": rays_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.head == "fp32" else "f32 (basis/shading GEMMs on tcgen05: bf16 operands, f32 accumulate)",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "warmup_requested": args.warmup,
+            "dtype": ("f32" if args.head == "fp32" else "f32 (basis/shading GEMMs on tcgen05: bf16 operands, f32 accumulate)") +
+                     ("; VM factors gathered from a bf16 copy (fp32 master parameters and gradients)" if args.storage == "bf16" else ""),
             "data": "synthetic",
             "config": {"workload": jt.synth.describe(args.workload, N) +
                                    f" ({n_views} views x {R_pix} pixels, rays generated from se3_refine + pose inside the step), "
                                    "fwd+bwd to factor/basis/head/se3 gradients, optimizer step excluded",
-                       "head": args.head,
+                       "head": args.head, "factor_storage": args.storage, "rays_per_gpu": N,
                        "head_arith": "forward: hi+lo split bf16 operands (3 MMAs per product, fp32-class, rgb within 1e-4); "
                                      "backward: bf16 operands, f32 accumulate (gradients within 2e-2 rel)",
                        "blur": args.blur, "l2": "256 MB write between timed steps (L2 flushed)",
@@ -663,9 +843,107 @@ def own_arm(args):
         dist.destroy_process_group()
 
 
+def render_arm(args):
+    """BASELINE configs[4]: --frames full 800x800 views of the 300^3 field, image-sharded over the ranks (rank r
+    renders frames r, r + W, ...: parallel.frames_of_rank, the slicing of nerf.py:728-740 per frame), no
+    collective on the data path. value = ms per frame = (max over ranks of the device time for its frames) / frames.
+    e2e: every frame's pose comes from pinned host memory and its rgb image goes back to the host."""
+    import torch.distributed as dist
+
+    import joint_tensorf_b200 as jt
+    from joint_tensorf_b200 import parallel
+    from joint_tensorf_b200.options import default_opt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload if args.workload in ("cfg2", "cfg2_sh") else "cfg2"
+    kw, run = jt.synth.config(wl)
+    kw = dict(kw)
+    torch.manual_seed(0)
+    model = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), dev, **kw)
+    model.head_precision = args.head
+    model.factor_storage = args.storage
+    opt = default_opt(model.shadingMode, False)
+    H_img = W_img = 800
+    n_pix = H_img * W_img
+    poses_h, intr = jt.synth.blender_views(args.frames, (H_img, W_img), seed=11)
+    poses_h = poses_h.pin_memory()
+    kinv = intr[:1].inverse().to(dev)
+    cam_opt = jt.options.Namespace(H=H_img, W=W_img, camera=dict(model="perspective", ndc=False), arch=dict())
+    rkw = dict(white_bg=True, is_train=False, ndc_ray=False, N_samples=run["n_samples"])
+    chunk = args.render_chunk
+    mine = parallel.frames_of_rank(args.frames, rank, world)
+    img_h = torch.empty((n_pix, 3), pin_memory=True)
+
+    def render_frame(pose_d):
+        outs = []
+        with torch.no_grad():
+            for c in range(0, n_pix, chunk):
+                ce, ra = jt.camera.get_center_and_ray(cam_opt, pose_d, kinv, pix_base=c, n_rays=min(chunk, n_pix - c))
+                outs.append(model(opt, ce.view(-1, 3), ra.view(-1, 3), **rkw)[0])
+        return torch.cat(outs)
+
+    def run_all(e2e):
+        finite = True
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        poses_d = poses_h.to(dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s_ev.record()
+        for f in mine:
+            pose = poses_h[f:f + 1].to(dev, non_blocking=True) if e2e else poses_d[f:f + 1]
+            img = render_frame(pose)
+            if e2e:
+                img_h.copy_(img, non_blocking=True)
+        e_ev.record()
+        torch.cuda.synchronize()
+        finite = bool(torch.isfinite(img).all()) if mine else True
+        t = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), finite
+
+    for f in mine[:max(1, min(args.warmup, 3))]:
+        render_frame(poses_h[f:f + 1].to(dev))
+    l0 = jt._lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms, finite = run_all(False)
+        launches = jt._lib.launch_count() - l0
+        ms_e2e, _ = run_all(True)
+    if rank == 0:
+        line = {"metric": RENDER_METRIC, "value": ms / args.frames, "unit": "ms/frame", "n_gpus": world,
+                "steps": args.frames, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms / args.frames,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (MLP_Fea inference GEMMs: fp16 operands on tcgen05, f32 accumulate)" if wl == "cfg2" else
+                         "f32 (basis GEMM: hi+lo bf16 operands on tcgen05)",
+                "data": "synthetic",
+                "config": {"workload": jt.synth.describe(wl) + f", {args.frames} hemisphere views at 800x800, is_train=False, "
+                                       f"{chunk} rays per forward call, frames dealt round-robin to the ranks",
+                           "frames_per_rank": len(mine), "head": args.head, "factor_storage": args.storage,
+                           "parallelism": f"image-sharded x{world}, no collective on the data path",
+                           "l2": "each frame streams 640 000 rays x ~650 samples: working set >> L2"},
+                "e2e": {"value": ms_e2e / args.frames, "unit": "ms/frame", "h2d_bytes_per_step": 48,
+                        "d2h_bytes_per_step": n_pix * 12, "ms_per_step": ms_e2e / args.frames},
+                "rays_per_s": args.frames * n_pix / (ms * 1e-3), "single_gpu_ms_per_frame_rank0": ms * world / args.frames
+                if world > 1 else ms / args.frames, "finite": finite, "gpu_launches": int(launches),
+                "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         reference_arm(a)
+    elif a.mode == "render":
+        render_arm(a)
     else:
         own_arm(a)

@@ -57,15 +57,17 @@ class RenderCfg:
         self.__dict__.update(kw)
 
 
-def tc_supported(cfg, afs=None, raise_if_not=False):
-    """The tensor-core head is specialised for the Blender-config head: MLP_Fea, app_dim 27,
-    hidden 64, fea_pe = view_pe = 2, 144 appearance components."""
+def tc_supported(cfg, afs=None, raise_if_not=False, comps=None):
+    """The tensor-core heads are specialised for the shipped configurations: Blender = 3 x 48 appearance
+    components, app_dim 27, MLP_Fea (hidden 64, fea_pe = view_pe = 2) or SH shading."""
+    comps = list(afs.C) if afs is not None else (list(comps) if comps is not None else None)
+    c48 = comps is None or all(int(c) == 48 for c in comps)
     ok = (cfg.shading == "MLP_Fea" and cfg.app_dim == 27 and cfg.hidden == 64 and cfg.fea_pe == 2 and
-          cfg.view_pe == 2 and (afs is None or afs.ctot == 144))
-    ok = ok or (cfg.shading == "SH" and cfg.app_dim == 27 and (afs is None or afs.ctot == 144))
+          cfg.view_pe == 2 and c48)
+    ok = ok or (cfg.shading == "SH" and cfg.app_dim == 27 and c48)
     if not ok and raise_if_not:
-        raise _lib.JtError("head='tc' needs MLP_Fea (hidden 64, pe 2) or SH shading with app_dim 27 and 144 "
-                           "components; use head='fp32'")
+        raise _lib.JtError("head='tc' needs 3 x 48 appearance components, app_dim 27 and MLP_Fea (hidden 64, pe 2) or "
+                           "SH shading; use head='fp32'")
     return ok
 
 

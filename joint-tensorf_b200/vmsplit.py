@@ -535,9 +535,7 @@ class B200_VMSplit(torch.nn.Module):
             fea_pe=int(self.fea_pe), view_pe=int(self.view_pe), hidden=int(self.featureC),
             fea_prog=float(fea_pe_progress), view_prog=float(view_pe_progress), tc_fwd_split=int(self.tc_fwd_split),
             tc_infer_fp16=bool(self.tc_infer_fp16))
-        from .render import tc_supported
-        if self.head_precision == "tc" or (self.head_precision == "auto" and tc_supported(cfg) and
-                                           sum(self.app_n_comp) == 144):
+        if self.head_precision == "tc" or (self.head_precision == "auto" and self.tc_available()):
             cfg.head = "tc"
 
         cfg.grad_sync = self.grad_sync
@@ -548,6 +546,14 @@ class B200_VMSplit(torch.nn.Module):
                               self.basis_mat.weight, *head)
 
     render = forward      # north_star calls the entry point `render`; the reference engine calls forward
+
+    def tc_available(self):
+        """True when the tcgen05 shading-head kernels cover this configuration (what head_precision="auto" picks):
+        exactly 48 appearance components per plane with app_dim 27 and MLP_Fea (hidden 64, pe 2) or SH shading."""
+        from .render import tc_supported
+        cfg = RenderCfg(shading=self.shadingMode, app_dim=int(self.app_dim), fea_pe=int(self.fea_pe),
+                        view_pe=int(self.view_pe), hidden=int(self.featureC))
+        return tc_supported(cfg, comps=self.app_n_comp)
 
     def _check_opt(self, opt):
         arch = opt.arch

@@ -1,6 +1,8 @@
 """Summarise an .ncu-rep: key metrics per kernel and (optionally) the top stall lines.
-usage: python scripts/ncu_summary.py rep.ncu-rep [--top N] [--kernel REGEX]"""
-import csv, subprocess, sys, io, re, collections
+usage: python scripts/ncu_summary.py rep.ncu-rep [--top N] [--kernel REGEX] [--json WORKLOAD:STORAGE --commit SHA]
+--json merges {name, time_ms, dram_read, dram_write, l1_lsu_wavefront_pct, regs} of every kernel (first launch of each
+name) into profiles/ncu_kernels.json under that key: bench.py reads `roofline.traffic` from there."""
+import csv, subprocess, sys, io, re, collections, json, os
 rep = sys.argv[1]
 top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 0
 kre = sys.argv[sys.argv.index("--kernel") + 1] if "--kernel" in sys.argv else None
@@ -16,6 +18,33 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 names = []
+if "--json" in sys.argv:
+    key = sys.argv[sys.argv.index("--json") + 1]
+    commit = sys.argv[sys.argv.index("--commit") + 1] if "--commit" in sys.argv else None
+    def num(r, k, scale=1.0):
+        if k not in hdr or not r[hdr.index(k)]:
+            return None
+        v, u = float(r[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
+        mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u, 1.0)
+        return v * mult * scale
+    seen, ks = set(), []
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if name in seen:
+            continue
+        seen.add(name)
+        ks.append({"name": name, "time_ms": num(r, "gpu__time_duration.sum"), "dram_read": num(r, "dram__bytes_read.sum"),
+                   "dram_write": num(r, "dram__bytes_write.sum"),
+                   "l1_lsu_wavefront_pct": num(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+                   "lts_hit_pct": num(r, "lts__t_sector_hit_rate.pct"), "regs": num(r, "launch__registers_per_thread"),
+                   "warps_active_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                   "dram_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_kernels.json")
+    db = json.load(open(out)) if os.path.exists(out) else {}
+    db[key] = {"file": os.path.basename(rep), "commit": commit, "kernels": ks}
+    json.dump(db, open(out, "w"), indent=1)
+    print("wrote", out, key, len(ks), "kernels")
+    sys.exit(0)
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
     names.append(name)

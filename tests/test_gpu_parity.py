@@ -1,21 +1,23 @@
 """GPU parity against golden vectors of the live reference and against the CPU oracle.
 
 Tolerances (BASELINE.json north_star): valid masks / sample indices bit-exact;
-rgb, depth, opacity <= 1e-4 max-abs (fp32); gradients <= 1e-4 max-abs AND
-<= 1e-3 of the largest gradient entry (the relative bound is the one that bites,
-SURVEY.md A.12; fp32 atomics reorder sums)."""
+rgb, depth, opacity <= 1e-4 max-abs (fp32); gradients <= 1e-4 of the largest gradient
+entry with the strict-fp32 head (fp32 atomics reorder sums, the
+measured errors are ~1e-6 and are logged to gpurun_out/parity_errors.jsonl by every
+test), <= 2e-2 with the tensor-core head whose backward GEMMs take bf16 operands."""
 import pytest
 import torch
 
 import joint_tensorf_b200 as jt
 from common import (field_from_golden, golden_names, golden_valid, load_golden, rel_err,
                     render_kwargs_from_golden, vo)
-from gpu_common import default_opt, forward_kwargs, module_from_golden, run_module_on_golden
+from gpu_common import (default_opt, forward_kwargs, module_from_golden, record_err, run_module_on_golden,
+                        slice_parity)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ABS_TOL = 1e-4
-GRAD_REL_TOL = 1e-3
+GRAD_REL_TOL = 1e-4
 # tensor-core head ("tc"): forward with split bf16 operands is fp32-class (<= 1e-4); its backward
 # GEMMs are plain bf16 -> the north star's bf16 tolerance, <= 2e-2 relative
 TC_GRAD_REL_TOL = 2e-2
@@ -58,6 +60,10 @@ def test_sample_mask_and_indices_bit_exact(name):
 def test_forward_backward_matches_reference_golden(name):
     g = load_golden(name)
     out = run_module_on_golden(g, DEV)
+    record_err("golden:" + name, head="fp32", rgb=(out["rgb"].cpu() - g["rgb"]).abs().max(),
+               depth=(out["depth"].cpu() - g["depth"]).abs().max(),
+               d_rays_o=rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]), d_rays_d=rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]),
+               **{"g:" + k: rel_err(out["grads"][k].cpu(), ref) for k, ref in g["grads"].items()})
     assert (out["rgb"].cpu() - g["rgb"]).abs().max() <= ABS_TOL
     assert (out["acc"].cpu() - g["acc"]).abs().max() <= ABS_TOL
     assert (out["depth"].cpu() - g["depth"]).abs().max() <= ABS_TOL
@@ -76,6 +82,9 @@ def test_tensor_core_head_on_reference_golden():
     """cubic_mlp golden (16/48 comps, MLP_Fea 64) through the tcgen05 head."""
     g = load_golden("cubic_mlp")
     out = run_module_on_golden(g, DEV, head="tc")
+    record_err("golden:cubic_mlp", head="tc", rgb=(out["rgb"].cpu() - g["rgb"]).abs().max(),
+               d_rays_o=rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]), d_rays_d=rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]),
+               **{"g:" + k: rel_err(out["grads"][k].cpu(), ref) for k, ref in g["grads"].items()})
     assert (out["rgb"].cpu() - g["rgb"]).abs().max() <= ABS_TOL
     assert (out["acc"].cpu() - g["acc"]).abs().max() <= ABS_TOL
     assert rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]) <= TC_GRAD_REL_TOL
@@ -89,6 +98,9 @@ def test_tensor_core_sh_on_reference_golden():
     gather + basis_mat + SHRender kernel and the tcgen05 SH backward."""
     g = load_golden("sh_vm48")
     out = run_module_on_golden(g, DEV, head="tc")
+    record_err("golden:sh_vm48", head="tc", rgb=(out["rgb"].cpu() - g["rgb"]).abs().max(),
+               d_rays_o=rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]), d_rays_d=rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]),
+               **{"g:" + k: rel_err(out["grads"][k].cpu(), ref) for k, ref in g["grads"].items()})
     assert (out["rgb"].cpu() - g["rgb"]).abs().max() <= ABS_TOL
     assert (out["acc"].cpu() - g["acc"]).abs().max() <= ABS_TOL
     assert (out["depth"].cpu() - g["depth"]).abs().max() <= ABS_TOL
@@ -185,10 +197,14 @@ def test_midsize_against_oracle(blur, head):
     assert torch.equal(acc_inf, acc.detach())
 
 
-@pytest.mark.parametrize("head,wl", [("fp32", "cfg2"), ("tc", "cfg2"), ("tc", "cfg2_sh")])
-def test_full_size_cfg2_properties(head, wl):
-    """300^3 / 4096 rays / S=1000 (the benchmark workloads: SH shading = BASELINE configs[1], and the MLP_Fea
-    head on the same field): size-independent invariants."""
+@pytest.mark.parametrize("head,wl,blur", [("fp32", "cfg2", None), ("tc", "cfg2", None), ("tc", "cfg2_sh", None),
+                                          ("fp32", "cfg2_sh", None), ("fp32", "cfg2", (0.09, 0.15)),
+                                          ("tc", "cfg2", (0.09, 0.15)), ("tc", "cfg2_sh", (0.09, 0.15))])
+def test_full_size_cfg2_properties(head, wl, blur):
+    """300^3 / 4096 rays / S=1000 (the benchmark workloads: SH shading = BASELINE configs[1], the MLP_Fea head on
+    the same field = configs[2], and both with the per-step blur of configs[2] at the benchmark's sigma
+    parameters 0.15 colour / 0.15 x 0.6 density): size-independent invariants + a 48-ray slice against the CPU
+    oracle for rgb / depth / opacity and ALL gradients (factors through the adjoint blur, basis_mat, head, rays)."""
     kw, run = jt.synth.config(wl)
     shading = kw["shadingMode"]
     torch.manual_seed(0)
@@ -203,6 +219,11 @@ def test_full_size_cfg2_properties(head, wl):
     o, d = o.to(DEV), d.to(DEV)
     S = run["n_samples"]
     jit = torch.rand(4096, device=DEV)
+    bkw, okw_b = {}, {}
+    if blur:
+        bkw = dict(c2f_mode="uniform-gaussian", c2f_parameter_density=blur[0], c2f_parameter_color=blur[1],
+                   c2f_kernel_size=64)
+        okw_b = dict(blur_mode="uniform-gaussian", blur_density=blur[0], blur_color=blur[1], kernel_size=64)
     # (1) compaction: sorted, unique, per-ray counts == dense mask popcount
     pts, z, valid = m.sample_ray(o, d, is_train=True, N_samples=S, jitter=jit)
     comp = jt.ops.march_compact(o, d, jit.contiguous(), False, S, m._h_geom(), None)
@@ -212,9 +233,11 @@ def test_full_size_cfg2_properties(head, wl):
     assert bool((sidx[1:] > sidx[:-1]).all())
     assert torch.equal(sidx.long(), torch.nonzero(valid.reshape(-1)).reshape(-1))
     assert 0.5 < v / (4096 * S) < 0.8
+    del pts, z
     # (2) render: weights + background transmittance partition unity; rgb in [0,1]
     og, dg = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
-    rgb, depth, acc = m.forward(default_opt(shading), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit)
+    rgb, depth, acc = m.forward(default_opt(shading), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit,
+                                **bkw)
     assert bool(((rgb >= 0) & (rgb <= 1)).all()) and bool(((acc >= -1e-5) & (acc <= 1 + 1e-4)).all())
     assert torch.isfinite(depth).all()
     # (3) linearity of the backward pass in the upstream gradient
@@ -224,22 +247,70 @@ def test_full_size_cfg2_properties(head, wl):
     gb = torch.autograd.grad((rgb * w2).sum(), params + [og], retain_graph=True)
     gc = torch.autograd.grad((rgb * (w1 + 2 * w2)).sum(), params + [og])
     for a, b, c in zip(ga, gb, gc):
-        assert rel_err(a + 2 * b, c) <= gtol
-    # (4) a 48-ray slice of the same full-size field against the CPU oracle
+        assert rel_err(a + 2 * b, c) <= max(gtol, 1e-3)          # self-consistency (atomics reorder the sums)
+    del rgb, depth, acc, ga, gb, gc
+    # (4) a 48-ray slice of the same full-size field against the CPU oracle, every gradient
     sl = slice(100, 148)
-    params = {k: v.detach().cpu().contiguous().clone() for k, v in m.state_dict().items()}
-    field = vo.Field(aabb=m.aabb.cpu(), grid=[300] * 3, params=params, near_far=[2.0, 6.0], step_ratio=0.5,
-                     density_shift=-10.0, distance_scale=25.0, weight_thres=1e-6, act="softplus", shading=shading)
-    oc = o[sl].cpu().clone().requires_grad_(True)
-    rgb_ref, depth_ref, acc_ref = vo.render(field, oc, d[sl].cpu(), n_samples=S, white_bg=True,
-                                            jitter=jit[sl].cpu().reshape(-1, 1))
-    (rgb_ref * w1[sl].cpu()).sum().backward()
-    assert (rgb[sl].detach().cpu() - rgb_ref).abs().max() <= ABS_TOL
-    assert (depth[sl].cpu() - depth_ref).abs().max() <= 2e-4
-    og2 = o[sl].clone().requires_grad_(True)
-    rgb2 = m.forward(default_opt(shading), og2, d[sl], white_bg=True, is_train=True, N_samples=S, jitter=jit[sl])[0]
-    (rgb2 * w1[sl]).sum().backward()
-    assert rel_err(og2.grad.cpu(), oc.grad) <= gtol
+    fkw = dict(opt=default_opt(shading), white_bg=True, is_train=True, N_samples=S, jitter=jit[sl], bg_coin=False, **bkw)
+    okw = dict(n_samples=S, white_bg=True, jitter=jit[sl].cpu().reshape(-1, 1), **okw_b)
+    field_kw = dict(aabb=m.aabb.cpu(), grid=[300] * 3, near_far=[2.0, 6.0], step_ratio=0.5, density_shift=-10.0,
+                    distance_scale=25.0, weight_thres=1e-6, act="softplus", shading=shading)
+    slice_parity(m, field_kw, o, d, jit, sl, fkw, okw, head, f"full:{wl}:blur={blur}", ABS_TOL, gtol, vo, rel_err)
+
+
+@pytest.mark.parametrize("near,blur,head", [(-1.0, None, "fp32"), (0.4, None, "fp32"), (-1.0, (0.09, 0.15), "fp32"),
+                                            (0.4, (0.09, 0.15), "fp32")])
+def test_full_size_cfg4_properties(near, blur, head):
+    """BASELINE configs[3] at size: LLFF NDC rays (1008x756 views), 617x687x617 grid, 3x16 / 3x20 components,
+    MLP_Fea_WeakView 32 head, relu density, S=1000, both ends of tensorf_near_plane_schedule (near 0.4 and -1);
+    blur on exercises the non-cubic H/W re-interpretation of bateRF.py:21-39,68,76 (SURVEY B-3) at 617x687.
+    Compaction bit-exact against the dense mask; a 64-ray slice against the CPU oracle with every gradient."""
+    kw, run = jt.synth.config("cfg4")
+    kw = dict(kw)
+    kw["near_far"] = [near, 1.0]
+    grid = list(kw["gridSize"])
+    torch.manual_seed(0)
+    m = jt.B200_VMSplit(torch.tensor(kw.pop("aabb")), kw.pop("gridSize"), DEV, **kw)
+    m.head_precision = head
+    gtol = GRAD_REL_TOL if head == "fp32" else TC_GRAD_REL_TOL
+    S = run["n_samples"]
+    o, d, _ = jt.synth.llff_ndc_rays(4096, 8)
+    o, d = o.to(DEV), d.to(DEV)
+    jit = torch.rand(1, S, generator=torch.Generator().manual_seed(3)).to(DEV)
+    bkw, okw_b = {}, {}
+    if blur:
+        bkw = dict(c2f_mode="uniform-gaussian", c2f_parameter_density=blur[0], c2f_parameter_color=blur[1],
+                   c2f_kernel_size=64)
+        okw_b = dict(blur_mode="uniform-gaussian", blur_density=blur[0], blur_color=blur[1], kernel_size=64)
+    # (1) compaction == nonzero(dense mask), bit-exact, sorted
+    pts, z, valid = m.sample_ray_ndc(o, d, is_train=True, N_samples=S, jitter=jit)
+    aux = (m._ndc_table(S, False) + jit.reshape(-1) * ((1.0 - near) / S)).contiguous()
+    comp = jt.ops.march_compact(o, d, aux, True, S, m._h_geom(), None)
+    v = int(comp.count.item())
+    assert v == int(valid.sum()) and v > 0.5 * 4096 * S
+    assert torch.equal(comp.sidx[:v].long(), torch.nonzero(valid.reshape(-1)).reshape(-1))
+    off = comp.ray_off
+    assert torch.equal((off[1:] - off[:-1]).long(), valid.sum(-1))
+    del pts, z, valid, comp
+    # (2) the full batch renders: finite, in range, appearance census in the expected class
+    og, dg = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    opt = default_opt("MLP_Fea_WeakView", True)
+    rgb, depth, acc = m.forward(opt, og, dg, white_bg=False, is_train=True, ndc_ray=True, N_samples=S, jitter=jit,
+                                bg_coin=False, **bkw)
+    a_cnt = int(jt.VMRender.last_counts[1].item())
+    record_err(f"full:cfg4:near={near}:blur={blur}", head=head, V=v, A=a_cnt)
+    assert bool(((rgb >= 0) & (rgb <= 1)).all()) and torch.isfinite(depth).all() and 0 < a_cnt < v
+    rgb.sum().backward()
+    assert torch.isfinite(og.grad).all() and torch.isfinite(m.app_plane[1].grad).all()
+    del rgb, depth, acc
+    # (3) 64-ray slice (8 rays of every view) against the CPU oracle, every gradient
+    sl = torch.arange(0, 4096, 64, device=DEV)
+    fkw = dict(opt=opt, white_bg=False, is_train=True, ndc_ray=True, N_samples=S, jitter=jit, bg_coin=False, **bkw)
+    okw = dict(n_samples=S, white_bg=False, jitter=jit.cpu(), ndc=True, **okw_b)
+    field_kw = dict(aabb=m.aabb.cpu(), grid=grid, near_far=[near, 1.0], step_ratio=0.3, density_shift=0.0,
+                    distance_scale=25.0, weight_thres=1e-7, act="relu", shading="MLP_Fea_WeakView")
+    slice_parity(m, field_kw, o, d, jit, sl, fkw, okw, head, f"full:cfg4:near={near}:blur={blur}", ABS_TOL, gtol,
+                 vo, rel_err)
 
 
 def test_empty_and_degenerate_batches():

@@ -16,6 +16,6 @@ timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu-basel
 tail -1 gpurun_out/${TAG}_bench_cfg4.log | cut -c1-300
 timeout 300 python bench.py --workload cfg2 --blur 0.15 --steps 10 --warmup 3 --no-cpu-baseline --no-render --no-also > gpurun_out/${TAG}_bench_cfg3.log 2>&1
 tail -1 gpurun_out/${TAG}_bench_cfg3.log | cut -c1-300
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"vm_scatter_walk|app_basis_fwd|vm_fwd_kernel|sh_bwd_data|head_bwd_wgrad|alpha_fwd|composite_fwd|render_bwd|march" -s 80 -c 12 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"vm_scatter_walk|app_basis_fwd|vm_fwd_kernel|sh_bwd_data|head_bwd_wgrad|alpha_fwd|composite_fwd|render_bwd|march" -s 44 -c 12 \
    -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-breakdown --no-render --no-also > gpurun_out/${TAG}_prof.log 2>&1
 ls -la gpurun_out | tail -5

@@ -20,7 +20,9 @@
  *  - VM factors are channel-last: plane i is [H_i][W_i][C_i], line i is [L_i][C_i]
  *    (the physical layout of a torch [1,C,H,W] tensor in channels_last format);
  *    h_factors = {plane0, plane1, plane2, line0, line1, line2};
- *    h_dims    = {H0,H1,H2, W0,W1,W2, L0,L1,L2, C0,C1,C2}; C_i % 4 == 0.
+ *    h_dims    = {H0,H1,H2, W0,W1,W2, L0,L1,L2, C0,C1,C2, elem}; C_i % 4 == 0; elem = 0: the factor pointers
+ *    address fp32 elements, 1: bf16 elements (the gather-side copy made by jt_cast_bf16_multi; accepted by
+ *    jt_vm_gather_fwd, jt_vm_scatter_rays, jt_app_basis_*_fwd_tc; gradients and arithmetic stay fp32).
  *    Plane i is sampled at (x = u[mat0_i] -> W axis, y = u[mat1_i] -> H axis) with
  *    matMode = [[0,1],[0,2],[1,2]], line i at u[vecMode_i], vecMode = [2,1,0]
  *    (tensorBase.py:405-406).
@@ -341,6 +343,13 @@ int jt_render_loss_fwd(const float* rgb, const float* images, const void* mask, 
 int jt_render_loss_bwd(const float* rgb, const float* images, const void* mask, int mask_kind, const int* ray_idx,
                        const int* view_idx, int n_views, int n_rays, int hw, int mode, float edge_factor,
                        float non_edge_factor, const double* ws4, const float* g_loss, float* d_rgb,
+                       cudaStream_t stream);
+
+/* ---- bf16 factor storage -------------------------------------------------- */
+/* dst[i][j] = bf16(src[i][j]) (round to nearest even) for n_arrays <= 12 contiguous arrays of h_count[i] elements
+ * (multiples of 4; src 16-byte, dst 8-byte aligned), ONE launch. Makes the gather-side bf16 copy of the VM factors
+ * (reference: fp32 Parameters tensoRF.py:159-169 sampled by F.grid_sample; north star: "bf16/fp32 gathers"). */
+int jt_cast_bf16_multi(int n_arrays, const void* const* h_src, void* const* h_dst, const long long* h_count,
                        cudaStream_t stream);
 
 #ifdef __cplusplus

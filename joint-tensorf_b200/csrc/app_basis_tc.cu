@@ -36,7 +36,7 @@ __device__ __forceinline__ uint2 pack4_bf16(float4 v) { return make_uint2(pack_b
 // SH = true: the epilogue also shades the sample with SHRender (tensorBase.py:68-72,
 // eval_sh_bases(2, .) sh.py:88-113): rgb = relu(sum_k Y_k(dir) feat[c*9+k] + 0.5); only the
 // view direction (for the backward) and rgb leave the kernel, the 27 features never do.
-template <int SPLIT, bool SAVE, bool SH>
+template <int SPLIT, bool SAVE, bool SH, bool B16>
 __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const float4* __restrict__ samp,
                                                               const int* __restrict__ aidx, const int* __restrict__ sidx,
                                                               const float* __restrict__ rays_d, int S, int normalize_dir,
@@ -84,19 +84,19 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
             const Tap tx = make_tap(u[mat0(i)], F.W[i]), ty = make_tap(u[mat1(i)], F.H[i]), tl = make_tap(u[vecm(i)], F.L[i]);
             const size_t C = CT / 3;
             const size_t r0 = (size_t)ty.i0 * F.W[i], r1 = (size_t)ty.i1 * F.W[i];
-            const float* p00 = F.plane[i] + (r0 + tx.i0) * C + sub * 4;
-            const float* p10 = F.plane[i] + (r0 + tx.i1) * C + sub * 4;
-            const float* p01 = F.plane[i] + (r1 + tx.i0) * C + sub * 4;
-            const float* p11 = F.plane[i] + (r1 + tx.i1) * C + sub * 4;
-            const float* l0 = F.line[i] + (size_t)tl.i0 * C + sub * 4;
-            const float* l1 = F.line[i] + (size_t)tl.i1 * C + sub * 4;
+            const size_t p00 = (r0 + tx.i0) * C + sub * 4, p10 = (r0 + tx.i1) * C + sub * 4;     // element offsets
+            const size_t p01 = (r1 + tx.i0) * C + sub * 4, p11 = (r1 + tx.i1) * C + sub * 4;
+            const size_t l0 = (size_t)tl.i0 * C + sub * 4, l1 = (size_t)tl.i1 * C + sub * 4;
+            const float* P = F.plane[i];
+            const float* Ln = F.line[i];
             const float w00 = tx.w0 * ty.w0, w10 = tx.w1 * ty.w0, w01 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float4 a, b, c, d, la, lb;
                 if (live) {
-                    a = ldg4(p00 + 16 * k); b = ldg4(p10 + 16 * k); c = ldg4(p01 + 16 * k); d = ldg4(p11 + 16 * k);
-                    la = ldg4(l0 + 16 * k); lb = ldg4(l1 + 16 * k);
+                    a = ld_tap4<B16>(P, p00 + 16 * k); b = ld_tap4<B16>(P, p10 + 16 * k);
+                    c = ld_tap4<B16>(P, p01 + 16 * k); d = ld_tap4<B16>(P, p11 + 16 * k);
+                    la = ld_tap4<B16>(Ln, l0 + 16 * k); lb = ld_tap4<B16>(Ln, l1 + 16 * k);
                 } else {
                     a = b = c = d = la = lb = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -199,14 +199,16 @@ static int app_basis_launch(int split, int sh, const void* const* h_factors, con
     int grid = (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
     unsigned char* st = static_cast<unsigned char*>(stage);
     g_launches += 1;
-#define JT_LAUNCH_G(SP, SV, SHV)                                                                                     \
+#define JT_LAUNCH_GB(SP, SV, SHV, BV)                                                                                \
     {                                                                                                                \
         const int smem = GSmem<SP>::total;                                                                           \
-        if (int rc = set_smem(app_basis_fwd_kernel<SP, SV, SHV>, smem)) return rc;                                   \
-        app_basis_fwd_kernel<SP, SV, SHV><<<grid, GT, smem, stream>>>(F, reinterpret_cast<const float4*>(samp),      \
-                                                                      aidx, sidx, rays_d, n_samples, normalize_dir,  \
-                                                                      Wb, n_dev, n_max, featdir, rgb, st);           \
+        if (int rc = set_smem(app_basis_fwd_kernel<SP, SV, SHV, BV>, smem)) return rc;                               \
+        app_basis_fwd_kernel<SP, SV, SHV, BV><<<grid, GT, smem, stream>>>(F, reinterpret_cast<const float4*>(samp),  \
+                                                                          aidx, sidx, rays_d, n_samples,             \
+                                                                          normalize_dir, Wb, n_dev, n_max, featdir,  \
+                                                                          rgb, st);                                  \
     }
+#define JT_LAUNCH_G(SP, SV, SHV) { if (F.bf16) JT_LAUNCH_GB(SP, SV, SHV, true) else JT_LAUNCH_GB(SP, SV, SHV, false) }
 #define JT_LAUNCH_GS(SP, SV) { if (sh) JT_LAUNCH_G(SP, SV, true) else JT_LAUNCH_G(SP, SV, false) }
     if (split == 1 && !st) JT_LAUNCH_GS(1, false)
     else if (split == 1) JT_LAUNCH_GS(1, true)
@@ -214,6 +216,7 @@ static int app_basis_launch(int split, int sh, const void* const* h_factors, con
     else JT_LAUNCH_GS(2, true)
 #undef JT_LAUNCH_GS
 #undef JT_LAUNCH_G
+#undef JT_LAUNCH_GB
     JT_RETURN_LAUNCH();
 }
 

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
             float q = 1.0f, alpha = 0.f, z = 0.f;
             if (j < e) {
                 float sigma = density_act(csf + shift, act);
-                alpha = 1.0f - expf(-sigma * (cdj * dscale));
+                alpha = 1.0f - exp_neg(-sigma * (cdj * dscale));
                 q = 1.0f - alpha + 1e-10f;
                 z = cz;
             }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
                 const float x = sf + shift;
                 const float sigma = density_act(x, act);
                 const float dd = dj * dscale;
-                const float ex = expf(-sigma * dd);
+                const float ex = exp_neg(-sigma * dd);
                 const float alpha = 1.0f - ex;
                 const float q = 1.0f - alpha + 1e-10f;
                 const float dalpha = dw * tj - suffix / q;

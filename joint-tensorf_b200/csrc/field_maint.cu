@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) field_alpha_kernel(Factors F, Geom G, Mas
         acc = quad_sum(acc);
         if (act && sub == 0) {
             float sigma = keep ? density_act(acc + A.shift, A.act) : 0.0f;
-            alpha[e] = 1.0f - expf(-sigma * A.length);
+            alpha[e] = 1.0f - exp_neg(-sigma * A.length);
         }
     }
 }
@@ -184,6 +184,7 @@ extern "C" int jt_field_alpha(const void* const* h_factors, const int* h_dims, c
     JT_CHECK_ARG(act == 0 || act == 1);
     Factors F;
     if (int rc = fill_factors(F, h_factors, h_dims)) return rc;
+    if (F.bf16) return JT_ERR_UNSUPPORTED;          // maintenance reads the fp32 master factors
     AlphaArgs A{};
     A.xyz = xyz;
     if (xyz) {

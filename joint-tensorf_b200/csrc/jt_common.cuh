@@ -43,6 +43,8 @@ struct Factors {
     int H[3], W[3], L[3], C[3];
     int off[3];           // channel offset of plane i in the concatenated feature vector
     int ctot;
+    int bf16;             // element type the plane / line pointers address: 0 fp32, 1 bf16 (a gather-side copy of
+                          // the fp32 master factors; offsets are in elements either way)
 };
 struct FactorGrads {
     float* plane[3];
@@ -74,6 +76,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// four bf16 (8 bytes) -> float4: a bf16 is the upper half of the fp32 with the same value
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 h) {
+    return make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u),
+                       __uint_as_float(h.y << 16), __uint_as_float(h.y & 0xFFFF0000u));
+}
+// one channel quad of a factor tap: `base` addresses fp32 or (B16) bf16 elements, `off` is an element offset
+template <bool B16>
+__device__ __forceinline__ float4 ld_tap4(const float* base, size_t off) {
+    if (B16) return bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(base) + off)));
+    return __ldg(reinterpret_cast<const float4*>(base + off));
+}
+
 // 1-D linear interpolation setup on an axis of n texels, align_corners=True,
 // zero padding (ATen grid_sampler semantics): index = (g+1)/2*(n-1).
 struct Tap {
@@ -100,7 +114,7 @@ __device__ __forceinline__ Tap make_tap(float g, int n) {
     return t;
 }
 
-// host: unpack the C-ABI factor description (include/jt_vm.h "Layouts")
+// host: unpack the C-ABI factor description (include/jt_vm.h "Layouts"); dims[12] = element type (0 fp32, 1 bf16)
 inline int fill_factors(Factors& F, const void* const* ptrs, const int* dims) {
     int off = 0;
     for (int i = 0; i < 3; ++i) {
@@ -113,6 +127,7 @@ inline int fill_factors(Factors& F, const void* const* ptrs, const int* dims) {
         off += F.C[i];
     }
     F.ctot = off;
+    F.bf16 = dims[12] ? 1 : 0;
     return JT_OK;
 }
 

@@ -23,7 +23,7 @@ namespace jt {
 
 // APP == false: out[e] = sum_i sum_c P_ic * L_ic               (density feature)
 // APP == true : out[e][off_i + c] = P_ic * L_ic                (appearance components, before basis_mat)
-template <bool APP>
+template <bool APP, bool B16>
 __global__ void __launch_bounds__(256, 4) vm_fwd_kernel(Factors F, const float4* __restrict__ samp,
                                                      const int* __restrict__ slot, const int* __restrict__ n_dev,
                                                      int n_fixed, float* __restrict__ out) {
@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(256, 4) vm_fwd_kernel(Factors F, const float4*
                 const PlaneTaps t = plane_taps(F, i, u);
                 const int C = F.C[i];
                 for (int q = sub * 4; q < C; q += 16) {
-                    float4 a = ldg4(t.p00 + q), b = ldg4(t.p10 + q), c = ldg4(t.p01 + q), d = ldg4(t.p11 + q);
-                    float4 la = ldg4(t.l0 + q), lb = ldg4(t.l1 + q);
+                    float4 a = ld_tap4<B16>(F.plane[i], t.o00 + q), b = ld_tap4<B16>(F.plane[i], t.o10 + q);
+                    float4 c = ld_tap4<B16>(F.plane[i], t.o01 + q), d = ld_tap4<B16>(F.plane[i], t.o11 + q);
+                    float4 la = ld_tap4<B16>(F.line[i], t.ol0 + q), lb = ld_tap4<B16>(F.line[i], t.ol1 + q);
                     float4 pv = f4_bilin(a, t.w00, b, t.w10, c, t.w01, d, t.w11);
                     float4 lv = f4_lerp2(la, t.tl.w0, lb, t.tl.w1);
                     if (APP) {
@@ -163,10 +164,11 @@ extern "C" int jt_vm_gather_fwd(int app, const void* const* h_factors, const int
     if (int rc = fill_factors(F, h_factors, h_dims)) return rc;
     int grid = grid_for(n_max);
     g_launches += 1;
-    if (app)
-        vm_fwd_kernel<true><<<grid, 256, 0, stream>>>(F, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max, out);
-    else
-        vm_fwd_kernel<false><<<grid, 256, 0, stream>>>(F, reinterpret_cast<const float4*>(samp), slot, n_dev, n_max, out);
+    const float4* sp = reinterpret_cast<const float4*>(samp);
+    if (app && F.bf16) vm_fwd_kernel<true, true><<<grid, 256, 0, stream>>>(F, sp, slot, n_dev, n_max, out);
+    else if (app) vm_fwd_kernel<true, false><<<grid, 256, 0, stream>>>(F, sp, slot, n_dev, n_max, out);
+    else if (F.bf16) vm_fwd_kernel<false, true><<<grid, 256, 0, stream>>>(F, sp, slot, n_dev, n_max, out);
+    else vm_fwd_kernel<false, false><<<grid, 256, 0, stream>>>(F, sp, slot, n_dev, n_max, out);
     JT_RETURN_LAUNCH();
 }
 
@@ -177,6 +179,7 @@ extern "C" int jt_vm_gather_bwd(int app, const void* const* h_factors, void* con
     if (n_max <= 0) return JT_OK;
     Factors F;
     if (int rc = fill_factors(F, h_factors, h_dims)) return rc;
+    if (F.bf16) return JT_ERR_UNSUPPORTED;          // the standalone feature ops differentiate the fp32 master factors
     FactorGrads G;
     for (int i = 0; i < 3; ++i) {
         G.plane[i] = static_cast<float*>(h_factor_grads[i]);

@@ -94,6 +94,9 @@ constexpr int SC_THREADS = 128;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -105,22 +108,30 @@ struct StepPos {          // tap position of one sample on one plane/line pair
     int sid;              // ray * S + k
 };
 
-template <bool APP, int NQ, int I, bool GB16, int THR = SC_THREADS>
+// B16: the factor taps are bf16 (8-byte quads: half the staging traffic), everything else is unchanged -- the
+// gradients and the arithmetic stay fp32.
+template <bool APP, int NQ, int I, bool GB16, bool B16, int THR = SC_THREADS>
 __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
-                                           int& ray, int& ray_end, RaySums& rs, float4* __restrict__ sm) {
+                                           int& ray, int& ray_end, RaySums& rs, unsigned char* __restrict__ sm) {
     const Factors& F = A.F;
     constexpr int ax = I == 2 ? 1 : 0, ay = I == 0 ? 1 : 2, al = 2 - I;      // matMode / vecMode (tensorBase.py:405-406)
     const int W = F.W[I], H = F.H[I], L = F.L[I], C = F.C[I];
     if (q >= C) return;
-    const float* __restrict__ P = F.plane[I] + q;
-    const float* __restrict__ Ln = F.line[I] + q;
+    constexpr int TS = B16 ? 8 : 16, ES = B16 ? 2 : 4;          // bytes per staged quad / per factor element
+    const unsigned char* __restrict__ P = reinterpret_cast<const unsigned char*>(F.plane[I]) + (size_t)q * ES;
+    const unsigned char* __restrict__ Ln = reinterpret_cast<const unsigned char*>(F.line[I]) + (size_t)q * ES;
     float* __restrict__ GP = A.G.plane[I] + q;
     float* __restrict__ GL = A.G.line[I] + q;
     const float sclx = 0.5f * (float)(W - 1), scly = 0.5f * (float)(H - 1), scll = 0.5f * (float)(L - 1);
     // this lane's staging slots (float4 index = slot * SC_THREADS): plane buffer b, tap c, quad k -> (b*4 + c)*NQ + k;
     // line buffer b, tap c, quad k -> 8 NQ + (b*2 + c)*NQ + k
-    auto pslot = [&](int b, int c, int k) -> float4* { return sm + ((b * 4 + c) * NQ + k) * THR; };
-    auto lslot = [&](int b, int c, int k) -> float4* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * THR; };
+    auto pslot = [&](int b, int c, int k) -> unsigned char* { return sm + ((b * 4 + c) * NQ + k) * (THR * TS); };
+    auto lslot = [&](int b, int c, int k) -> unsigned char* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * (THR * TS); };
+    auto rd = [&](const unsigned char* p) -> float4 {
+        if (B16) return bf16x4_to_f4(*reinterpret_cast<const uint2*>(p));
+        return *reinterpret_cast<const float4*>(p);
+    };
+    auto cp = [&](unsigned char* dst, const unsigned char* src) { if (B16) cp_async8(dst, src); else cp_async16(dst, src); };
 
     auto make_pos = [&](const float4 u4, const int sid) {
         const float u[3] = {u4.x, u4.y, u4.z};
@@ -147,13 +158,13 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) cp_async16(pslot(b, c, k), P + o[c] + k * qs);
+            for (int k = 0; k < NQ; ++k) cp(pslot(b, c, k), P + (size_t)(o[c] + k * qs) * ES);
     };
     auto fetch_line = [&](int b, const unsigned o[2]) {
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) cp_async16(lslot(b, c, k), Ln + o[c] + k * qs);
+            for (int k = 0; k < NQ; ++k) cp(lslot(b, c, k), Ln + (size_t)(o[c] + k * qs) * ES);
     };
     // upstream gradient of element e for this lane's quads: fetched raw one step ahead (the
     // conversion happens at use, so the load latency stays off the issue path)
@@ -293,8 +304,8 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
         float2 dA2 = dup2(0.f), dB2 = dup2(0.f), dC2 = dup2(0.f), dD2 = dup2(0.f), dLa2 = dup2(0.f), dLb2 = dup2(0.f);
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
-            const float4 a = *pslot(pb, 0, k), b = *pslot(pb, 1, k), c = *pslot(pb, 2, k), d = *pslot(pb, 3, k);
-            const float4 la = *lslot(lb, 0, k), lb4 = *lslot(lb, 1, k);
+            const float4 a = rd(pslot(pb, 0, k)), b = rd(pslot(pb, 1, k)), c = rd(pslot(pb, 2, k)), d = rd(pslot(pb, 3, k));
+            const float4 la = rd(lslot(lb, 0, k)), lb4 = rd(lslot(lb, 1, k));
             float4 pv = f4_scale(a, w00), lv = f4_scale(la, wl0p);
             f4_fma(pv, b, w10); f4_fma(pv, c, w01); f4_fma(pv, d, w11);
             f4_fma(lv, lb4, wl1p);
@@ -332,16 +343,16 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
     flush_ray();
 }
 
-template <bool APP, int NQ, int MINB, bool GB16, int LWC>
+template <bool APP, int NQ, int MINB, bool GB16, int LWC, bool B16>
 __global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
-    extern __shared__ __align__(16) float4 sc_smem[];      // 12 NQ slots x SC_THREADS float4
+    extern __shared__ __align__(16) unsigned char sc_smem[];   // 12 NQ slots x SC_THREADS quads (16 B fp32 / 8 B bf16)
     const int LW = LWC > 0 ? LWC : LW_rt;                // lanes per walker (compile-time strides when LWC > 0)
     const int n = A.n_dev ? *A.n_dev : A.n_fixed;
     const int wl = threadIdx.x / LW;                     // walker within the CTA
     const int q = (threadIdx.x - wl * LW) * 4;           // first channel of this lane's first quad
     const int qs = LW * 4;                               // channel stride between this lane's quads
     if (wl >= walkers_per_cta) return;
-    float4* sm = sc_smem + threadIdx.x;
+    unsigned char* sm = sc_smem + threadIdx.x * (B16 ? 8 : 16);
     const int stride = gridDim.x * walkers_per_cta;      // walkers in the grid
     // Segment length. The grid is persistent (one wave of resident CTAs) and the units are dealt round-robin, so the
     // kernel takes ceil(units / walkers) rounds: a fixed length leaves up to a whole round idle at the end (measured
@@ -361,9 +372,9 @@ __global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const
         RaySums rs;
 #pragma unroll
         for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
-        walk_plane<APP, NQ, 0, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
-        walk_plane<APP, NQ, 1, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
-        walk_plane<APP, NQ, 2, GB16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        walk_plane<APP, NQ, 0, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        walk_plane<APP, NQ, 1, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        walk_plane<APP, NQ, 2, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
     }
 }
 
@@ -421,20 +432,22 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     if (A.seg_target > 0) want = cap;                         // one resident wave; the kernel sizes the segments to fit
     int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     g_launches += 1;
-    const int smem = 12 * nq * SC_THREADS * 16;
-#define JT_SC(APPV, NQV, MB, GB, LWV)                                                                              \
+    const int smem = 12 * nq * SC_THREADS * (A.F.bf16 ? 8 : 16);
+#define JT_SCB(APPV, NQV, MB, GB, LWV, BV)                                                                          \
     {                                                                                                               \
         if (smem > 48 * 1024 &&                                                                                     \
-            cudaFuncSetAttribute(vm_scatter_walk_kernel<APPV, NQV, MB, GB, LWV>,                                    \
+            cudaFuncSetAttribute(vm_scatter_walk_kernel<APPV, NQV, MB, GB, LWV, BV>,                                \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)                 \
             return JT_ERR_LAUNCH;                                                                                   \
-        vm_scatter_walk_kernel<APPV, NQV, MB, GB, LWV><<<grid, threads, smem, stream>>>(A, LW, wpc);                \
+        vm_scatter_walk_kernel<APPV, NQV, MB, GB, LWV, BV><<<grid, threads, smem, stream>>>(A, LW, wpc);            \
     }
+#define JT_SC(APPV, NQV, MB, GB, LWV) { if (A.F.bf16) JT_SCB(APPV, NQV, MB, GB, LWV, true) else JT_SCB(APPV, NQV, MB, GB, LWV, false) }
     // (64-thread CTAs with a 200-register cap -- five CTAs per SM instead of two -- spill and lose: 1.55 vs 1.22 ms;
     // a minimum-blocks bound of 3 (168 registers) likewise: 2.28 ms.)
     if (app && gin_bf16) { if (nq == 3) JT_SC(true, 3, 2, true, 4) else if (nq == 2) JT_SC(true, 2, 3, true, 4) else JT_SC(true, 1, 3, true, 0) }
     else if (app) { if (nq == 3) JT_SC(true, 3, 2, false, 4) else if (nq == 2) JT_SC(true, 2, 3, false, 4) else JT_SC(true, 1, 3, false, 0) }
     else { if (nq == 3) JT_SC(false, 3, 2, false, 4) else if (nq == 2) JT_SC(false, 2, 3, false, 4) else JT_SC(false, 1, 4, false, 0) }
 #undef JT_SC
+#undef JT_SCB
     JT_RETURN_LAUNCH();
 }

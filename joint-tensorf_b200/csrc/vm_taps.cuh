@@ -42,6 +42,14 @@ __device__ __forceinline__ PlaneTaps plane_taps(const Factors& F, int i, const f
     return t;
 }
 
+// exp(x) for x <= 0 as the reference's alpha = 1 - exp(-sigma*dist) needs it (tensorBase.py:59): for a thin
+// medium (x ~ -1e-4, every sample of a freshly initialised Blender field) alpha is the distance of exp(x) from 1 in
+// units of 2^-24, so ONE ulp of exp() is 3e-4 of alpha. CUDA's expf is within 2 ulp but biased by ~0.3 ulp in this
+// range (measured: every weight / appearance gradient of the 300^3 field was 1.7e-4 off the CPU reference, whose
+// vectorised exp is correctly rounded 96 % of the time). 1 + expm1f(x) is a single rounding of an exact-enough
+// increment, i.e. the correctly rounded exp(x), for |x| < 0.1; beyond that the amplification is gone.
+__device__ __forceinline__ float exp_neg(float x) { return x > -0.1f ? 1.0f + expm1f(x) : expf(x); }
+
 __device__ __forceinline__ float density_act(float x, int act) {
     // act 0: softplus (beta 1, threshold 20; ATen softplus), act 1: relu. x already includes the shift.
     if (act == 0) return x > 20.0f ? x : log1pf(expf(x));

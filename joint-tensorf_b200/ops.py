@@ -10,7 +10,7 @@ import contextlib
 import torch
 
 from . import _lib
-from ._lib import check, floats, ints, ptrs
+from ._lib import check, floats, ints, longlongs, ptrs
 
 MAT_MODE = ((0, 1), (0, 2), (1, 2))   # reference tensorBase.py:405
 VEC_MODE = (2, 1, 0)                  # reference tensorBase.py:406
@@ -76,19 +76,42 @@ def phys_cl(x):
 
 
 class FactorSet:
-    """Three planes + three lines in channel-last physical form and their dims."""
+    """Three planes + three lines in channel-last physical form and their dims. `store` (optional) is a list of
+    six bf16 buffers holding the same values: the kernels then gather from those (dims[12] = 1) while `planes` /
+    `lines` stay the fp32 tensors the gradients belong to."""
 
-    def __init__(self, planes, lines):
+    def __init__(self, planes, lines, store=None):
         self.planes = [phys_cl(p) for p in planes]            # [H,W,C]
         self.lines = [phys_cl(l)[:, 0, :] for l in lines]     # [L,C]
         self.C = [p.shape[2] for p in self.planes]
         for i in range(3):
             if self.C[i] % 4 != 0 or self.lines[i].shape[1] != self.C[i]:
                 raise _lib.JtError(f"component count {self.C[i]} must be a multiple of 4 and match its line")
+        self.store = store
         self.dims = ints([p.shape[0] for p in self.planes] + [p.shape[1] for p in self.planes] +
-                         [l.shape[0] for l in self.lines] + self.C)
-        self.ptrs = ptrs([p.data_ptr() for p in self.planes] + [l.data_ptr() for l in self.lines])
+                         [l.shape[0] for l in self.lines] + self.C + [1 if store is not None else 0])
+        src = store if store is not None else self.planes + self.lines
+        self.ptrs = ptrs([t.data_ptr() for t in src])
         self.ctot = sum(self.C)
+
+    def with_bf16_store(self, cache=None):
+        """The same factors with a bf16 gather-side copy (one jt_cast_bf16_multi launch). `cache`: dict reused
+        across calls; an entry is valid while the source tensor's storage and version counter are unchanged
+        (inference renders thousands of chunks from the same factors)."""
+        srcs = self.planes + self.lines
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+        if cache is not None and cache.get("key") == key:
+            store = cache["store"]
+        else:
+            store = [torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) for t in srcs]
+            cast_bf16_multi(srcs, store)
+            if cache is not None:
+                cache["key"], cache["store"] = key, store
+        fs = FactorSet.__new__(FactorSet)
+        fs.planes, fs.lines, fs.C, fs.ctot, fs.store = self.planes, self.lines, self.C, self.ctot, store
+        fs.dims = ints(list(self.dims)[:12] + [1])
+        fs.ptrs = ptrs([t.data_ptr() for t in store])
+        return fs
 
     def zero_grads(self):
         gp = [torch.zeros_like(p) for p in self.planes]
@@ -100,6 +123,17 @@ class FactorSet:
         """physical [H,W,C] / [L,C] gradients -> logical [1,C,H,W] / [1,C,L,1] views."""
         return ([g.unsqueeze(0).permute(0, 3, 1, 2) for g in gp],
                 [g.unsqueeze(0).unsqueeze(2).permute(0, 3, 1, 2) for g in gl])
+
+
+def cast_bf16_multi(srcs, dsts):
+    """dsts[i] = bf16(srcs[i]) for up to 12 contiguous fp32 arrays in one launch (csrc/factor_store.cu)."""
+    for a, b in zip(srcs, dsts):
+        _need_cuda(a, "factor")
+        assert a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.bfloat16
+    with TIMER.span("cast_bf16"):
+        check(_lib.lib().jt_cast_bf16_multi(len(srcs), ptrs([a.data_ptr() for a in srcs]),
+                                            ptrs([b.data_ptr() for b in dsts]), longlongs([a.numel() for a in srcs]),
+                                            _stream()), "jt_cast_bf16_multi")
 
 
 # ------------------------------------------------------------------ K1

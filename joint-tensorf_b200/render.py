@@ -54,6 +54,8 @@ class RenderCfg:
         self.tc_fwd_split = 2       # 2: hi+lo bf16 operands (fp32-class forward), 1: plain bf16
         self.grad_enabled = True    # torch.is_grad_enabled() at the call site (B200_VMSplit.forward sets it)
         self.tc_infer_fp16 = True   # no-grad forward of the MLP_Fea head: single-term fp16 operands (rgb within ~2e-5)
+        self.storage = "fp32"       # "bf16": the kernels gather from a bf16 copy of the factors (fp32 masters / gradients)
+        self.store_cache = (None, None)
         self.__dict__.update(kw)
 
 
@@ -167,6 +169,9 @@ class VMRender(torch.autograd.Function):
         basis_w = basis_w.detach().contiguous()
         dfs = FactorSet([t.detach() for t in dens[:3]], [t.detach() for t in dens[3:]])
         afs = FactorSet([t.detach() for t in app[:3]], [t.detach() for t in app[3:]])
+        if cfg.storage == "bf16":
+            dfs = dfs.with_bf16_store(cfg.store_cache[0])
+            afs = afs.with_bf16_store(cfg.store_cache[1])
         N, S = rays_o.shape[0], cfg.n_samples
         F = cfg.app_dim
         ldf = _r4(F)

@@ -140,10 +140,16 @@ class B200_VMSplit(torch.nn.Module):
                  fea_pe=6, featureC=128, step_ratio=2.0, fea2denseAct="softplus", dtype=torch.float32,
                  volume_init_scale=0.1, volume_init_bias=0.1):
         super().__init__()
-        if dtype != torch.float32:
-            raise _lib.JtError("B200_VMSplit keeps fp32 master factors (dtype must be torch.float32)")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise _lib.JtError("B200_VMSplit: dtype must be torch.float32 or torch.bfloat16 (bf16 factor storage)")
         self.device = device
-        self.dtype = dtype
+        # bf16 factor storage (north star: "bf16/fp32 gathers", <= 2e-2 relative class): the Parameters stay fp32
+        # master copies (optimizer state, checkpoints and gradients are unchanged); the gather / scatter kernels read
+        # their taps from a bf16 copy refreshed when a factor changes (csrc/factor_store.cu). Selected with
+        # dtype=torch.bfloat16 at construction or by setting `factor_storage = "bf16"` afterwards.
+        self.factor_storage = "bf16" if dtype == torch.bfloat16 else "fp32"
+        self._store_cache = ({}, {})          # bf16 copies of the density / appearance factors (no-blur calls)
+        self.dtype = torch.float32
         self.alphaMask = alphaMask
         self.matMode = [list(m) for m in MAT_MODE]
         self.vecMode = list(VEC_MODE)
@@ -540,6 +546,12 @@ class B200_VMSplit(torch.nn.Module):
 
         cfg.grad_sync = self.grad_sync
         cfg.grad_enabled = torch.is_grad_enabled()
+        if self.factor_storage not in ("fp32", "bf16"):
+            raise _lib.JtError(f"factor_storage {self.factor_storage!r}: expected 'fp32' or 'bf16'")
+        cfg.storage = self.factor_storage
+        # the bf16 copies are cached per (storage, version) only for the module's own Parameters: blurred factors
+        # are fresh buffers every call (an address + version key could alias a previous step's buffer)
+        cfg.store_cache = self._store_cache if self.kernel_density is None and self.kernel_color is None else (None, None)
         dp, dl, ap, al = self._blurred_all(self.kernel_density, self.kernel_color)
         head = self.renderModule.head_params() if self.renderModule is not None else []
         return VMRender.apply(cfg, center.reshape(-1, 3), ray_dir.reshape(-1, 3), aux, *dp, *dl, *ap, *al,
@@ -581,6 +593,7 @@ class B200_VMSplit(torch.nn.Module):
                 lines[i] = torch.nn.Parameter(ops.resize_bilinear_cl(lines[i].data, res_target[VEC_MODE[i]], 1))
         self.update_stepSize(res_target)
         self._reg_cache = None
+        self._store_cache = ({}, {})
 
     def _dense_tables(self, gridSize):
         return [torch.linspace(0, 1, int(g)).to(self.device) for g in gridSize]
@@ -644,6 +657,7 @@ class B200_VMSplit(torch.nn.Module):
             new_aabb = corrected
         self.aabb = new_aabb
         self._reg_cache = None
+        self._store_cache = ({}, {})
         new_size = b_r - t_l
         self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
 

@@ -158,6 +158,7 @@ def blur_line(taps, line):
     """BAT_VMSplit.convolute_line, bateRF.py:8-19. line [1,C,L,1]."""
     c = line.shape[1]
     half = taps.shape[-1] // 2
+    taps = taps.to(line.dtype)
     x = line.squeeze(-1).view(c, 1, -1)
     x = F.pad(x, (half, half), mode="replicate")
     x = F.conv1d(x, taps.view(1, 1, -1))
@@ -171,7 +172,7 @@ def blur_plane(taps, plane, hh, ww):
     (SURVEY.md Appendix B-3). Reproduced, not fixed."""
     c = plane.shape[1]
     half = taps.shape[-1] // 2
-    k = taps.view(1, 1, -1)
+    k = taps.to(plane.dtype).view(1, 1, -1)
     x = plane.reshape(c, hh, ww)
     x = F.pad(x, (half, half), mode="replicate")
     x = F.conv1d(x, k.expand(hh, 1, -1), groups=hh)
@@ -205,7 +206,7 @@ def _factors(field, fc, prefix, taps):
 def density_feature(field, fc, u, taps=None):
     """BAT_VMSplit.compute_densityfeature, bateRF.py:41-94 (all arch flags False)."""
     cp, cl = _plane_line_grids(u)
-    sig = torch.zeros((u.shape[0],))
+    sig = torch.zeros((u.shape[0],), dtype=u.dtype)
     for i, (p, l) in enumerate(_factors(field, fc, "density", taps)):
         pc = F.grid_sample(p, cp[[i]], mode="bilinear", align_corners=True).view(-1, u.shape[0])
         lc = F.grid_sample(l, cl[[i]], mode="bilinear", align_corners=True).view(-1, u.shape[0])
@@ -238,7 +239,7 @@ def feature2density(field, x):
 def raw2alpha(sigma, dist):
     """tensorBase.py:57-65."""
     alpha = 1.0 - torch.exp(-sigma * dist)
-    t = torch.cumprod(torch.cat([torch.ones(alpha.shape[0], 1), 1.0 - alpha + 1e-10], -1), -1)
+    t = torch.cumprod(torch.cat([torch.ones(alpha.shape[0], 1, dtype=alpha.dtype), 1.0 - alpha + 1e-10], -1), -1)
     return alpha, alpha * t[:, :-1], t[:, -1:]
 
 
@@ -322,13 +323,19 @@ _SHADERS = {"MLP_Fea": shade_mlp_fea, "MLP_Fea_WeakView": shade_weakview, "SH": 
 # --------------------------------------------------------------------------- forward
 def render(field, rays_o, rays_d, *, n_samples, white_bg=True, jitter=None, ndc=False,
            blur_mode=None, blur_density=None, blur_color=None, kernel_size=None,
-           view_prog=1.0, fea_prog=1.0, detail=False):
+           view_prog=1.0, fea_prog=1.0, detail=False, exact=False):
     """BatBase.forward, batBase.py:44-165 (detach_viewdirs/detach_xyz True,
     two-stage / predict_density heads off, `bg coin flip` folded into white_bg).
 
     jitter: [N,1] (metric rays) or [1,S] (NDC) uniform numbers, None == is_train False.
     Differentiable w.r.t. field.params, rays_o, rays_d. Returns rgb[N,3],
-    depth[N], acc[N] (+ dict of intermediates when detail=True)."""
+    depth[N], acc[N] (+ dict of intermediates when detail=True).
+
+    exact=True (not the reference's arithmetic; a yardstick for it): the samples are placed in fp32
+    exactly as above -- the valid mask is the bit-exact class -- and everything after that runs in
+    float64 (field.params must be float64). The tests use it to tell a real discrepancy from the
+    reference's own fp32 rounding where a gradient is ill-conditioned (transmittance cancellation in
+    nearly opaque fields, 1 - exp(-x) for x ~ 1e-4)."""
     fc = grid_constants(field.aabb, field.grid, field.step_ratio)
     dirs = rays_d
     if ndc:
@@ -341,6 +348,8 @@ def render(field, rays_o, rays_d, *, n_samples, white_bg=True, jitter=None, ndc=
         pts, z, valid = sample_ray(fc, field.near_far, rays_o, dirs, n_samples, jitter)
         dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1)
     dirs = dirs.view(-1, 1, 3).expand(pts.shape).detach()     # detach_viewdirs
+    if exact:
+        pts, z, dists, dirs = pts.double(), z.double(), dists.double(), dirs.double()
 
     blur_on = blur_density is not None or blur_color is not None
     if field.mask_volume is not None and not blur_on:          # batBase.py:76-82
@@ -354,8 +363,8 @@ def render(field, rays_o, rays_d, *, n_samples, white_bg=True, jitter=None, ndc=
         taps_d = blur_taps(fc, blur_mode, blur_density, kernel_size)
         taps_c = blur_taps(fc, blur_mode, blur_color, kernel_size)
 
-    sigma = torch.zeros(pts.shape[:-1])
-    rgb = torch.zeros((*pts.shape[:2], 3))
+    sigma = torch.zeros(pts.shape[:-1], dtype=pts.dtype)
+    rgb = torch.zeros((*pts.shape[:2], 3), dtype=pts.dtype)
     u = normalize_coord(fc, pts)
     sig_feat = None
     if valid.any():

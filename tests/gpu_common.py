@@ -34,9 +34,15 @@ def forward_kwargs(g, device):
     return kw
 
 
-def run_module_on_golden(g, device="cuda:0", head="fp32"):
+def run_module_on_golden(g, device="cuda:0", head="fp32", storage="fp32", round_factors=False):
     m = module_from_golden(g, device)
     m.head_precision = head
+    m.factor_storage = storage
+    if round_factors:          # fp32 factors holding bf16-representable values
+        with torch.no_grad():
+            for plist in (m.density_plane, m.density_line, m.app_plane, m.app_line):
+                for p in plist:
+                    p.copy_(p.to(torch.bfloat16).float())
     o = g["rays_o"].to(device).requires_grad_(True)
     d = g["rays_d"].to(device).requires_grad_(True)
     opt = default_opt(g["case"]["shading"], g["case"].get("ndc", False))
@@ -67,37 +73,62 @@ def record_err(test, **vals):
         pass
 
 
-def slice_parity(m, field_kw, o, d, jit, sl, fkw, okw, head, tag, abs_tol, grad_tol, vo, rel_err, seed=4):
+def slice_parity(m, field_kw, o, d, jit, sl, fkw, okw, head, tag, abs_tol, grad_tol, vo, rel_err, seed=4, exact=None):
     """Render the ray slice `sl` of a full-size field on the GPU module `m` and with the CPU oracle on a copy of its
-    parameters; compare rgb / depth / opacity and EVERY gradient (12 factors, basis_mat, head, rays_o, rays_d)."""
+    parameters; compare rgb / depth / opacity and EVERY gradient (12 factors, basis_mat, head, rays_o, rays_d).
+
+    A gradient passes when it is within `grad_tol` of the oracle's fp32 result (the reference's arithmetic). Some
+    full-size gradients are ill-conditioned in fp32 -- the density gradient of a nearly opaque field is the
+    difference of two transmittance sums that cancel to ~1e-4 of their size, and alpha = 1 - exp(-x) for x ~ 1e-4
+    amplifies one ulp of exp() to 3e-4 -- so two correct fp32 implementations with different summation order differ
+    by more than 1e-4 there. For those (`exact` defaults to True with the fp32 head) the oracle is also run in
+    float64 on the same fp32-placed samples (vo.render(exact=True)) and the gradient must be no further from that
+    exact result than twice the reference's own fp32 rounding error: err(ours, f64) <= max(tol, 2 err(ref32, f64)).
+    All three numbers are logged per tensor."""
     dev = o.device
-    params = {k: v.detach().cpu().contiguous().clone().requires_grad_(True) for k, v in m.state_dict().items()
-              if not k.startswith("alphaMask")}
-    field = vo.Field(params=params, **field_kw)
-    os_, ds_ = o[sl].cpu().clone().requires_grad_(True), d[sl].cpu().clone().requires_grad_(True)
-    n = os_.shape[0]
+    exact = (head == "fp32") if exact is None else exact
+    sd = {k: v.detach().cpu().contiguous().clone() for k, v in m.state_dict().items() if not k.startswith("alphaMask")}
+    n = o[sl].shape[0]
     g = torch.Generator().manual_seed(seed)
     w_rgb, w_acc = torch.rand(n, 3, generator=g), torch.rand(n, generator=g)
-    rgb_ref, depth_ref, acc_ref = vo.render(field, os_, ds_, **okw)
-    ((rgb_ref * w_rgb).sum() + (acc_ref * w_acc).sum()).backward()
+
+    def run_oracle(dtype):
+        params = {k: v.to(dtype).requires_grad_(True) for k, v in sd.items()}
+        field = vo.Field(params=params, **field_kw)
+        os_, ds_ = o[sl].cpu().clone().requires_grad_(True), d[sl].cpu().clone().requires_grad_(True)
+        rgb_r, depth_r, acc_r = vo.render(field, os_, ds_, exact=(dtype == torch.float64), **okw)
+        ((rgb_r * w_rgb).sum() + (acc_r * w_acc).sum()).backward()
+        grads = {"d_rays_o": os_.grad, "d_rays_d": ds_.grad}
+        grads.update({"g:" + k: p.grad for k, p in params.items() if p.grad is not None})
+        return rgb_r.detach(), depth_r.detach(), acc_r.detach(), grads
+
+    rgb_ref, depth_ref, acc_ref, g32 = run_oracle(torch.float32)
+    g64 = run_oracle(torch.float64)[3] if exact else None
     for p in m.parameters():
         p.grad = None
     og, dg = o[sl].clone().requires_grad_(True), d[sl].clone().requires_grad_(True)
     m.head_precision = head
+    fkw = dict(fkw)
     rgb, depth, acc = m.forward(fkw.pop("opt"), og, dg, **fkw)
     ((rgb * w_rgb.to(dev)).sum() + (acc * w_acc.to(dev)).sum()).backward()
+    mine = {"d_rays_o": og.grad.cpu(), "d_rays_d": dg.grad.cpu()}
+    mine.update({"g:" + k: p.grad.cpu() for k, p in m.named_parameters() if p.grad is not None})
     errs = dict(rgb=(rgb.detach().cpu() - rgb_ref).abs().max(), acc=(acc.detach().cpu() - acc_ref).abs().max(),
-                depth=(depth.cpu() - depth_ref).abs().max(), d_rays_o=rel_err(og.grad.cpu(), os_.grad),
-                d_rays_d=rel_err(dg.grad.cpu(), ds_.grad))
-    for k, p in m.named_parameters():
-        ref = params[k].grad
-        if ref is None:
-            continue
-        assert p.grad is not None, k
-        errs["g:" + k] = rel_err(p.grad.cpu(), ref)
+                depth=(depth.cpu() - depth_ref).abs().max())
+    bad = {}
+    for k, ref in g32.items():
+        assert k in mine, k
+        e_ref = rel_err(mine[k], ref)
+        errs[k] = e_ref
+        ok = e_ref <= grad_tol
+        if exact:
+            e_exact, e_noise = rel_err(mine[k], g64[k]), rel_err(ref, g64[k])
+            errs[k + "|vs_f64"], errs[k + "|ref32_vs_f64"] = e_exact, e_noise
+            ok = ok or e_exact <= max(grad_tol, 2.0 * e_noise)
+        if not ok:
+            bad[k] = {kk: float(v) for kk, v in errs.items() if kk.startswith(k)}
     record_err(tag, head=head, **errs)
     assert errs["rgb"] <= abs_tol and errs["acc"] <= abs_tol, errs
     assert errs["depth"] <= 2 * abs_tol, errs
-    bad = {k: v for k, v in errs.items() if (k.startswith("g:") or k.startswith("d_rays")) and not v <= grad_tol}
     assert not bad, bad
     return errs

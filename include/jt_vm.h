@@ -345,6 +345,30 @@ int jt_render_loss_bwd(const float* rgb, const float* images, const void* mask, 
                        float non_edge_factor, const double* ws4, const float* g_loss, float* d_rgb,
                        cudaStream_t stream);
 
+/* ---- K3, tensor-core path of the LLFF head ---------------------------------- */
+/* basis_mat (bateRF.py:130, Linear 60 -> 20) + positional_encoding (tensorBase.py:43-55) +
+ * MLPRender_Fea_WeakView.forward (tensorBase.py:198-214) for 3 x 20 components, app_dim 20, hidden 32, fea_pe =
+ * view_pe = 2 (options/bat_llff_VM_MLP.yaml), on tcgen05 with hi + lo bf16 operand terms (fp32-class results).
+ * comps [n][60] fp32 = output of jt_vm_gather_fwd(app = 1); aidx / sidx / rays_d / n_samples / normalize_dir locate
+ * the view direction of appearance sample e (ray = sidx[aidx[e]] / n_samples; normalised for NDC rays,
+ * batBase.py:63-66). Outputs: rgb [n][4] (sigmoid colours, 4th float 0), featdir [n][32] (features 0..19, view
+ * direction 28..30: kept for the backward). stage = NULL (inference) or jt_wv_stage_bytes(n_max) bytes, 128-byte
+ * aligned: receives the bf16 operand tiles the backward GEMMs need. */
+long long jt_wv_stage_bytes(int n_max);
+int jt_wv_head_fwd_tc(const float* comps, const int* aidx, const int* sidx, const float* rays_d, int n_samples,
+                      int normalize_dir, const float* Wb, const float* W1, const float* b1, const float* W2,
+                      const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
+                      float fea_progress, float view_progress, float* featdir, float* rgb, void* stage,
+                      cudaStream_t stream);
+/* Autograd of the above (bf16-operand GEMMs, fp32 accumulation in TMEM). dout [n][4] = dL/d(pre-sigmoid) as
+ * jt_render_bwd writes it; dcomps [n][60] fp32 = gradient w.r.t. the gathered components (input of
+ * jt_vm_scatter_rays); the weight gradients are ACCUMULATED into gWb [20][60], gW1 [32][100], gb1 [32],
+ * gW2 [32][32], gb2 [32], gW3 [3][44], gb3 [3] (zero-initialised by the caller). */
+int jt_wv_head_bwd_tc(const float* dout, const float* featdir, const float* Wb, const float* W1, const float* W2,
+                      const float* W3, const int* n_dev, int n_max, float fea_progress, float* dcomps, void* stage,
+                      float* gWb, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                      cudaStream_t stream);
+
 /* ---- bf16 factor storage -------------------------------------------------- */
 /* dst[i][j] = bf16(src[i][j]) (round to nearest even) for n_arrays <= 12 contiguous arrays of h_count[i] elements
  * (multiples of 4; src 16-byte, dst 8-byte aligned), ONE launch. Makes the gather-side bf16 copy of the VM factors

@@ -49,6 +49,8 @@ SIGNATURES = {
     "jt_edge_mask": [_P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
     "jt_render_loss_fwd": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P],
     "jt_render_loss_bwd": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],
+    "jt_wv_head_fwd_tc": [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P],
+    "jt_wv_head_bwd_tc": [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_cast_bf16_multi": [_I, _P, _P, _P, _P],
     "jt_adam_multi": [_I, _P, _P, _P, _P, _P, _P, _P, _D, _D, _D, _D, _I, _P],
 }
@@ -79,6 +81,8 @@ def lib():
         cdll.jt_version.restype = _I
         cdll.jt_head_tc_stage_bytes.argtypes = [_I]
         cdll.jt_head_tc_stage_bytes.restype = ctypes.c_longlong
+        cdll.jt_wv_stage_bytes.argtypes = [_I]
+        cdll.jt_wv_stage_bytes.restype = ctypes.c_longlong
         cdll.jt_edge_mask_ws_floats.argtypes = [_I, _I, _I]
         cdll.jt_edge_mask_ws_floats.restype = ctypes.c_longlong
         cdll.jt_launch_count.argtypes = []

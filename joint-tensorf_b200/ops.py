@@ -301,6 +301,30 @@ def head_bwd_tc(dout, feat, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, 
               "jt_head_bwd_tc")
 
 
+def wv_stage(n_max, device):
+    """Scratch for the bf16 operand tiles exchanged between the WeakView tensor-core head kernels."""
+    nbytes = int(_lib.lib().jt_wv_stage_bytes(int(n_max)))
+    return torch.empty((nbytes,), device=device, dtype=torch.uint8)
+
+
+def wv_head_fwd_tc(comps, aidx, sidx, rays_d, n_samples, normalize_dir, wb, w1, b1, w2, b2, w3, b3, n_dev, n_max, fprog,
+                   vprog, featdir, rgb, stage=None):
+    """basis_mat + PE + MLPRender_Fea_WeakView on tensor cores (csrc/weakview_tc.cu): comps [A][60] -> rgb [A][4]."""
+    with TIMER.span("wv_head_fwd_tc"):
+        check(_lib.lib().jt_wv_head_fwd_tc(_p(comps), _p(aidx), _p(sidx), _p(rays_d), int(n_samples), int(normalize_dir),
+                                           _p(wb), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(n_dev), int(n_max),
+                                           float(fprog), float(vprog), _p(featdir), _p(rgb), _p(stage), _stream()),
+              "jt_wv_head_fwd_tc")
+
+
+def wv_head_bwd_tc(dout, featdir, wb, w1, w2, w3, n_dev, n_max, fprog, dcomps, stage, grads):
+    """grads = (gWb, gW1, gb1, gW2, gb2, gW3, gb3), zero-initialised by the caller; dcomps [A][60] fp32."""
+    with TIMER.span("wv_head_bwd_tc"):
+        check(_lib.lib().jt_wv_head_bwd_tc(_p(dout), _p(featdir), _p(wb), _p(w1), _p(w2), _p(w3), _p(n_dev), int(n_max),
+                                           float(fprog), _p(dcomps), _p(stage), *[_p(g) for g in grads], _stream()),
+              "jt_wv_head_bwd_tc")
+
+
 # ------------------------------------------------------------------ K5
 def host_taps(kernel):
     """Blur taps as a host float array (they travel in the kernel parameters / constant bank).

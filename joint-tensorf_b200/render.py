@@ -56,6 +56,7 @@ class RenderCfg:
         self.tc_infer_fp16 = True   # no-grad forward of the MLP_Fea head: single-term fp16 operands (rgb within ~2e-5)
         self.storage = "fp32"       # "bf16": the kernels gather from a bf16 copy of the factors (fp32 masters / gradients)
         self.store_cache = (None, None)
+        self.bf16_backward_taps = False
         self.__dict__.update(kw)
 
 
@@ -67,9 +68,14 @@ def tc_supported(cfg, afs=None, raise_if_not=False, comps=None):
     ok = (cfg.shading == "MLP_Fea" and cfg.app_dim == 27 and cfg.hidden == 64 and cfg.fea_pe == 2 and
           cfg.view_pe == 2 and c48)
     ok = ok or (cfg.shading == "SH" and cfg.app_dim == 27 and c48)
+    # LLFF = 3 x 20 components, app_dim 20, MLP_Fea_WeakView (hidden 32, fea_pe = view_pe = 2): csrc/weakview_tc.cu
+    c20 = comps is None or all(int(c) == 20 for c in comps)
+    ok = ok or (cfg.shading == "MLP_Fea_WeakView" and cfg.app_dim == 20 and cfg.hidden == 32 and cfg.fea_pe == 2 and
+                cfg.view_pe == 2 and c20)
     if not ok and raise_if_not:
         raise _lib.JtError("head='tc' needs 3 x 48 appearance components, app_dim 27 and MLP_Fea (hidden 64, pe 2) or "
-                           "SH shading; use head='fp32'")
+                           "SH shading, or 3 x 20 components, app_dim 20 and MLP_Fea_WeakView (hidden 32, pe 2); "
+                           "use head='fp32'")
     return ok
 
 
@@ -169,9 +175,16 @@ class VMRender(torch.autograd.Function):
         basis_w = basis_w.detach().contiguous()
         dfs = FactorSet([t.detach() for t in dens[:3]], [t.detach() for t in dens[3:]])
         afs = FactorSet([t.detach() for t in app[:3]], [t.detach() for t in app[3:]])
+        # bf16 factor storage: the forward gathers read the bf16 copy. The backward walks the fp32 factors unless
+        # cfg.bf16_backward_taps: the coordinate (pose) gradient is a DIFFERENCE of neighbouring texels, and on a blurred
+        # field bf16 rounding of two nearly equal neighbours costs more than the 2e-2 class allows (measured 2.7e-2 on
+        # d/d rays_o); the staged taps are not what binds the scatter kernel either (same time with 8-byte taps).
+        dfs32, afs32 = dfs, afs
         if cfg.storage == "bf16":
             dfs = dfs.with_bf16_store(cfg.store_cache[0])
             afs = afs.with_bf16_store(cfg.store_cache[1])
+            if cfg.bf16_backward_taps:
+                dfs32, afs32 = dfs, afs
         N, S = rays_o.shape[0], cfg.n_samples
         F = cfg.app_dim
         ldf = _r4(F)
@@ -200,7 +213,18 @@ class VMRender(torch.autograd.Function):
 
         ws = {}
         comps = None
-        if cfg.head == "tc":
+        if cfg.head == "tc" and cfg.shading == "MLP_Fea_WeakView":
+            tc_supported(cfg, afs, raise_if_not=True)
+            train = cfg.grad_enabled and any(ctx.needs_input_grad)
+            comps = torch.empty((cap, afs.ctot), device=dev)
+            ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
+            feat = torch.empty((cap, 32), device=dev)             # feat 0..19 | 0 | view dir 28..30 | 0
+            rgb = torch.empty((cap, 4), device=dev)
+            ws["stage"] = ops.wv_stage(cap, dev) if train else None
+            ops.wv_head_fwd_tc(comps, aidx, comp.sidx, rays_d, S, cfg.ndc, basis_w, *head, a_count, cap, cfg.fea_prog,
+                               cfg.view_prog, feat, rgb, ws["stage"])
+            comps = None                                          # the staged bf16 tile replaces it in the backward
+        elif cfg.head == "tc":
             tc_supported(cfg, afs, raise_if_not=True)
             rgb = torch.empty((cap, 4), device=dev)
             # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), and grad mode is always
@@ -237,7 +261,7 @@ class VMRender(torch.autograd.Function):
                                        int(cfg.white_bg), float(cfg.depth_bias), _p(rgb_pre), _p(rgb_map),
                                        _p(depth), _p(opacity), _stream()), "jt_composite_fwd")
 
-        ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws = cfg, comp, dfs, afs, ws
+        ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws = cfg, comp, dfs32, afs32, ws
         ctx.bufs = dict(rays_d=rays_d, sigfeat=sigfeat, weight=weight, trans=trans, app_off=app_off, aidx=aidx,
                         app_of=app_of, comps=comps, feat=feat, rgb=rgb, rgb_pre=rgb_pre, basis_w=basis_w, head=head,
                         a_count=a_count)
@@ -292,8 +316,14 @@ class VMRender(torch.autograd.Function):
             check(lib.jt_ray_init(_p(b["rays_d"]), _p(dnorm), N, _p(d_o), _p(d_d), _stream()), "jt_ray_init")
 
         # tensor-core head: dcomps crosses HBM as bf16 (its GEMM operands are bf16 already)
-        dcomps = torch.empty((cap, afs.ctot), device=dev, dtype=torch.bfloat16 if cfg.head == "tc" else torch.float32)
-        if cfg.head == "tc" and cfg.shading == "SH":
+        wv_tc = cfg.head == "tc" and cfg.shading == "MLP_Fea_WeakView"
+        dcomps = torch.empty((cap, afs.ctot), device=dev,
+                             dtype=torch.bfloat16 if (cfg.head == "tc" and not wv_tc) else torch.float32)
+        if wv_tc:
+            w1, b1, w2, b2, w3, b3 = b["head"]
+            ops.wv_head_bwd_tc(dout, b["feat"], b["basis_w"], w1, w2, w3, b["a_count"], cap, cfg.fea_prog, dcomps,
+                               ws["stage"], (g_basis, *head_grads))
+        elif cfg.head == "tc" and cfg.shading == "SH":
             ops.sh_bwd_tc(dout, b["feat"], b["basis_w"], b["a_count"], cap, dcomps, ws["stage"], g_basis)
         elif cfg.head == "tc":
             w1, b1, w2, b2, w3, b3 = b["head"]

@@ -549,6 +549,7 @@ class B200_VMSplit(torch.nn.Module):
         if self.factor_storage not in ("fp32", "bf16"):
             raise _lib.JtError(f"factor_storage {self.factor_storage!r}: expected 'fp32' or 'bf16'")
         cfg.storage = self.factor_storage
+        cfg.bf16_backward_taps = bool(getattr(self, "bf16_backward_taps", False))
         # the bf16 copies are cached per (storage, version) only for the module's own Parameters: blurred factors
         # are fresh buffers every call (an address + version key could alias a previous step's buffer)
         cfg.store_cache = self._store_cache if self.kernel_density is None and self.kernel_color is None else (None, None)
@@ -561,7 +562,8 @@ class B200_VMSplit(torch.nn.Module):
 
     def tc_available(self):
         """True when the tcgen05 shading-head kernels cover this configuration (what head_precision="auto" picks):
-        exactly 48 appearance components per plane with app_dim 27 and MLP_Fea (hidden 64, pe 2) or SH shading."""
+        3 x 48 appearance components with app_dim 27 and MLP_Fea (hidden 64, pe 2) or SH shading (Blender configs), or
+        3 x 20 components with app_dim 20 and MLP_Fea_WeakView (hidden 32, pe 2) (the LLFF config)."""
         from .render import tc_supported
         cfg = RenderCfg(shading=self.shadingMode, app_dim=int(self.app_dim), fea_pe=int(self.fea_pe),
                         view_pe=int(self.view_pe), hidden=int(self.featureC))

@@ -34,10 +34,11 @@ def forward_kwargs(g, device):
     return kw
 
 
-def run_module_on_golden(g, device="cuda:0", head="fp32", storage="fp32", round_factors=False):
+def run_module_on_golden(g, device="cuda:0", head="fp32", storage="fp32", round_factors=False, bf16_bwd_taps=False):
     m = module_from_golden(g, device)
     m.head_precision = head
     m.factor_storage = storage
+    m.bf16_backward_taps = bf16_bwd_taps
     if round_factors:          # fp32 factors holding bf16-representable values
         with torch.no_grad():
             for plist in (m.density_plane, m.density_line, m.app_plane, m.app_line):
@@ -93,7 +94,7 @@ def slice_parity(m, field_kw, o, d, jit, sl, fkw, okw, head, tag, abs_tol, grad_
     w_rgb, w_acc = torch.rand(n, 3, generator=g), torch.rand(n, generator=g)
 
     def run_oracle(dtype):
-        params = {k: v.to(dtype).requires_grad_(True) for k, v in sd.items()}
+        params = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
         field = vo.Field(params=params, **field_kw)
         os_, ds_ = o[sl].cpu().clone().requires_grad_(True), d[sl].cpu().clone().requires_grad_(True)
         rgb_r, depth_r, acc_r = vo.render(field, os_, ds_, exact=(dtype == torch.float64), **okw)

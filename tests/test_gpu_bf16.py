@@ -22,6 +22,7 @@ BF16_TOL = 2e-2
 def _heads(g):
     case = g["case"]
     tc = list(case["app"]) == [48, 48, 48] and case["app_dim"] == 27 and case["shading"] in ("MLP_Fea", "SH")
+    tc = tc or (list(case["app"]) == [20, 20, 20] and case["app_dim"] == 20 and case["shading"] == "MLP_Fea_WeakView")
     return ["fp32", "tc"] if tc else ["fp32"]
 
 
@@ -30,8 +31,10 @@ def test_bf16_storage_equals_fp32_kernels_on_rounded_factors(name):
     g = load_golden(name)
     if g["case"]["blur"] is not None:
         pytest.skip("with blur the bf16 copy is made from the blurred factors: no rounded-input twin")
-    for head in _heads(g):
-        a = run_module_on_golden(g, DEV, head=head, storage="bf16")
+    for head, bwd_taps in [(h, t) for h in _heads(g) for t in (False, True)]:
+        # bwd_taps: the scatter walker reads the bf16 copy too (vm_scatter_walk_kernel<..., B16 = true>)
+        a = run_module_on_golden(g, DEV, head=head, storage="bf16", round_factors=not bwd_taps,
+                                 bf16_bwd_taps=bwd_taps)
         b = run_module_on_golden(g, DEV, head=head, storage="fp32", round_factors=True)
         errs = dict(rgb=(a["rgb"] - b["rgb"]).abs().max(), depth=(a["depth"] - b["depth"]).abs().max(),
                     d_rays_o=rel_err(a["d_rays_o"], b["d_rays_o"]), d_rays_d=rel_err(a["d_rays_d"], b["d_rays_d"]))

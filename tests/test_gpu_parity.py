@@ -110,6 +110,25 @@ def test_tensor_core_sh_on_reference_golden():
         assert rel_err(out["grads"][k].cpu(), ref) <= TC_GRAD_REL_TOL, (k, rel_err(out["grads"][k].cpu(), ref))
 
 
+@pytest.mark.parametrize("name", ["ndc_weakview", "ndc_weakview_blur"])
+def test_tensor_core_weakview_on_reference_golden(name):
+    """LLFF-shaped goldens (3x16 / 3x20 comps, app_dim 20, MLP_Fea_WeakView 32, NDC rays, non-cubic grid) through
+    the tcgen05 WeakView head (csrc/weakview_tc.cu): hi+lo bf16 forward (fp32 class), bf16 backward GEMMs."""
+    g = load_golden(name)
+    out = run_module_on_golden(g, DEV, head="tc")
+    errs = dict(rgb=(out["rgb"].cpu() - g["rgb"]).abs().max(), acc=(out["acc"].cpu() - g["acc"]).abs().max(),
+                depth=(out["depth"].cpu() - g["depth"]).abs().max(),
+                d_rays_o=rel_err(out["d_rays_o"].cpu(), g["d_rays_o"]), d_rays_d=rel_err(out["d_rays_d"].cpu(), g["d_rays_d"]),
+                **{"g:" + k: rel_err(out["grads"][k].cpu(), ref) for k, ref in g["grads"].items()})
+    record_err("golden:" + name, head="tc", **errs)
+    assert errs["rgb"] <= ABS_TOL and errs["acc"] <= ABS_TOL and errs["depth"] <= ABS_TOL, errs
+    bad = {k: float(v) for k, v in errs.items() if k not in ("rgb", "acc", "depth") and v > TC_GRAD_REL_TOL}
+    assert not bad, bad
+    for k, (s, sabs, mx) in g["grad_sums"].items():
+        got = out["grads"][k].double().abs().sum().item()
+        assert abs(got - sabs) <= TC_GRAD_REL_TOL * max(sabs, 1e-12), (k, got, sabs)
+
+
 @pytest.mark.parametrize("head", ["fp32", "tc"])
 def test_midsize_sh_against_oracle(head):
     """128^3, 16/48 comps, SH shading, 300 rays (a ragged last tile): CUDA path vs the CPU oracle;
@@ -259,7 +278,7 @@ def test_full_size_cfg2_properties(head, wl, blur):
 
 
 @pytest.mark.parametrize("near,blur,head", [(-1.0, None, "fp32"), (0.4, None, "fp32"), (-1.0, (0.09, 0.15), "fp32"),
-                                            (0.4, (0.09, 0.15), "fp32")])
+                                            (0.4, (0.09, 0.15), "fp32"), (-1.0, None, "tc"), (0.4, (0.09, 0.15), "tc")])
 def test_full_size_cfg4_properties(near, blur, head):
     """BASELINE configs[3] at size: LLFF NDC rays (1008x756 views), 617x687x617 grid, 3x16 / 3x20 components,
     MLP_Fea_WeakView 32 head, relu density, S=1000, both ends of tensorf_near_plane_schedule (near 0.4 and -1);

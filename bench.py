@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--mode", default="train", choices=["train", "render"],
                     help="render = BASELINE configs[4]: --frames full 800x800 frames, image-sharded over the ranks, ms/frame")
     ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="N > 1: cap the CTAs NCCL may use (NCCL_MAX_CTAS) so the collectives leave SMs to the kernels "
+                         "they overlap with (0 = NCCL's default)")
     ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"],
                     help="VM factor storage the gathers read (fp32 master parameters either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -446,6 +449,8 @@ def own_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if args.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
     try:
@@ -501,8 +506,7 @@ def own_arm(args):
     params = [p for p in model.parameters()] + [se3_refine]
     # data parallel: the render node's backward reduces its flat gradient bucket across ranks itself (appearance
     # part overlapped with the density scatter); the loss carries the 1/world factor, so the sums are means
-    sync = parallel.OverlappedGradSync() if world > 1 else None
-    model.grad_sync = sync
+    sync = parallel.OverlappedGradSync().attach(model, [se3_refine]) if world > 1 else None
     inv_world = 1.0 / world
 
     def make_step(model, opt, params):
@@ -587,6 +591,23 @@ def own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    ddp_breakdown = None
+    if world > 1:
+        # where the data-parallel step spends its time: rank 0 records CUDA events around every C-ABI call and the
+        # gradient-synchronisation waits while ALL ranks run the same reduced steps (events do not synchronise)
+        ops.TIMER.enabled = rank == 0
+        for _ in range(2):
+            step(pix_d, tgt_d)
+        if rank == 0:
+            ops.TIMER.summary()
+        reps = 5
+        for _ in range(reps):
+            flush.fill_(1.0)
+            step(pix_d, tgt_d)
+        if rank == 0:
+            ddp_breakdown = {k: round(v[0] / reps, 4) for k, v in sorted(ops.TIMER.summary().items(), key=lambda kv: -kv[1][0])}
+        ops.TIMER.enabled = False
+        barrier()
     roof, breakdown = None, None
     if rank == 0 and not args.no_breakdown:
         ops.TIMER.enabled = True                 # rank-0-only section: no collectives in here
@@ -828,6 +849,8 @@ def own_arm(args):
             line["roofline"] = roof
         if breakdown is not None:
             line["kernel_ms_per_step"] = breakdown
+        if ddp_breakdown is not None:
+            line["kernel_ms_per_step_data_parallel_rank0"] = ddp_breakdown
         if render is not None:
             line["render_800x800"] = render
         if also is not None:

@@ -66,21 +66,65 @@ class GradBucket:
 class OverlappedGradSync:
     """Sum the gradients of a step across ranks while its backward is still running.
 
-    `B200_VMSplit.grad_sync = OverlappedGradSync()` makes the render node's backward hand over its flat gradient
+    `sync.attach(model)` (or `model.grad_sync = sync`) makes the render node's backward hand over its flat gradient
     bucket in two parts: the appearance-factor gradients (3/4 of the bytes, complete after the appearance scatter)
     are all-reduced on NCCL's stream while the density scatter runs; the rest (density factors, basis_mat, head)
     follows and the backward's stream waits for both before the node returns, so whatever consumes the gradients
     next (p.grad, the adjoint blur -- linear, so reducing before it is the same sum) sees cross-rank sums.
-    `finish(extra)` reduces the few gradients produced by later autograd nodes (se3_refine). Sums only: scale the
-    loss by 1/world_size for a mean (no extra pass over the bucket). World size 1: every call is a no-op."""
+    `finish(extra)` reduces the few gradients produced by later autograd nodes (se3_refine) in place.
+
+    Semantics (read this before writing a training loop):
+      * SUMS only. Scale the RENDER loss by 1/world_size for a mean: `(render_loss / world + regularisers).backward()`.
+        Gradients that reach the factors from other autograd nodes (density_L1 / TV_loss_* through FieldRegularizers)
+        or through `regularize_()` are NOT reduced -- they are identical on every rank (replicated parameters), so
+        they must carry their full single-GPU weight, not 1/world.
+      * every backward through the render node issues collectives while a synchroniser is attached: a backward that
+        only some ranks run (validation on rank 0, test-time pose optimisation) must run under `with sync.paused():`
+        or it hangs waiting for the other ranks.
+      * `attach()` broadcasts the parameters from rank 0, so the replicas start identical even if the ranks were
+        seeded differently.
+    World size 1: every call is a no-op."""
 
     def __init__(self, group=None):
         self.group = group
         self.works = []
         self.bytes = 0
+        self.enabled = True
 
     def _active(self):
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        return self.enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def attach(self, model, extra_params=()):
+        """Make `model` (B200_VMSplit) reduce its gradients through this object; broadcast its parameters (and
+        `extra_params`, e.g. se3_refine) from rank 0."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            with torch.no_grad():
+                for p in list(model.parameters()) + list(extra_params):
+                    # channel-last factors: broadcast the underlying storage order, not a contiguous copy
+                    buf = p.data.permute(0, 2, 3, 1) if (p.dim() == 4 and not p.data.is_contiguous()) else p.data
+                    if not buf.is_contiguous():
+                        tmp = buf.contiguous()
+                        dist.broadcast(tmp, 0, group=self.group)
+                        buf.copy_(tmp)
+                    else:
+                        dist.broadcast(buf, 0, group=self.group)
+                    if hasattr(torch.autograd.graph, "increment_version"):
+                        torch.autograd.graph.increment_version(p)      # refresh cached bf16 copies
+        model.grad_sync = self
+        return self
+
+    def paused(self):
+        """Context manager: backward passes inside it issue no collectives (rank-local work)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            prev, self.enabled = self.enabled, False
+            try:
+                yield self
+            finally:
+                self.enabled = prev
+        return cm()
 
     def _reduce(self, t):
         if self._active() and t.numel() > 0:
@@ -95,21 +139,24 @@ class OverlappedGradSync:
         self.wait()
 
     def wait(self):
-        for w in self.works:
-            w.wait()
+        if self.works:
+            from .ops import TIMER
+            with TIMER.span("grad_sync_wait"):     # device time the compute stream spends waiting for the collectives
+                for w in self.works:
+                    w.wait()
         self.works = []
 
     def finish(self, extra=()):
-        """extra: parameters whose .grad was produced outside the render node (e.g. se3_refine)."""
-        gs = [p.grad for p in extra if p.grad is not None]
-        if gs and self._active():
-            cat = torch.cat([g.reshape(-1) for g in gs])
-            self._reduce(cat)
-            self.wait()
-            o = 0
-            for g in gs:
-                g.copy_(cat[o:o + g.numel()].view_as(g))
-                o += g.numel()
+        """extra: parameters whose .grad was produced outside the render node (e.g. se3_refine): reduced in place,
+        one small collective each (no concatenation / copy-back kernels)."""
+        if self._active():
+            for p in extra:
+                if p.grad is not None:
+                    g = p.grad if p.grad.is_contiguous() else None
+                    if g is None:
+                        p.grad = p.grad.contiguous()
+                        g = p.grad
+                    self._reduce(g)
         self.wait()
 
 

@@ -292,11 +292,16 @@ class VMRender(torch.autograd.Function):
                                     int(cfg.white_bg), shade_act, _p(dout), _p(dsig), _p(dnorm), _stream()),
                   "jt_render_bwd")
 
+        if VMRender.debug_capture is not None:            # diagnostics (scripts/debug_cfg4_grad.py): per-sample gradients
+            VMRender.debug_capture.update(dsig=dsig.clone(), dout=dout.clone(), count=comp.count.clone())
+
         # One flat zero-filled bucket for every gradient this node produces (one memset; also the unit the
         # data-parallel all-reduce works on): [app planes, app lines | density planes, density lines | basis, head].
         # The appearance part comes first and is complete first, so a gradient synchroniser
         # (parallel.OverlappedGradSync) can reduce it across ranks while the density scatter still runs.
         sync = getattr(cfg, "grad_sync", None)
+        if sync is not None and not sync._active():       # world size 1, or inside `with sync.paused():`
+            sync = None
         shapes = [p.shape for p in afs.planes] + [l.shape for l in afs.lines] + \
                  [p.shape for p in dfs.planes] + [l.shape for l in dfs.lines] + \
                  [b["basis_w"].shape] + [t.shape for t in b["head"]]
@@ -357,4 +362,5 @@ class VMRender(torch.autograd.Function):
 
 
 VMRender.last_grad_bucket = None
+VMRender.debug_capture = None
 VMRender.last_counts = None

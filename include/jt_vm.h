@@ -106,11 +106,14 @@ int jt_vm_gather_bwd(int app, const void* const* h_factors, void* const* h_facto
  * count; > 0: the same with at most max_ctas CTAs; < 0: fixed segments of -max_ctas samples on a non-persistent
  * grid (leaves room for a collective running next to the kernel).
  * max_ctas > 0 caps the (persistent) grid, so that the kernel can share the SMs with another
- * kernel running on a second stream; 0 = fill the machine. */
+ * kernel running on a second stream; 0 = fill the machine.
+ * plane_mask: bit i = walk plane / line pair i in this launch (7 = all three in one launch). The data-parallel
+ * backward launches the appearance planes one by one so that each plane's gradients can be all-reduced while the
+ * next plane is still being walked. */
 int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads, const int* h_dims,
                        const float* samp, const int* slot, const int* sidx, const int* n_dev, int n_max,
                        const void* gin, int gin_bf16, int n_samples, const float* h_inv, float* d_o, float* d_d,
-                       int max_ctas, cudaStream_t stream);
+                       int max_ctas, int plane_mask, cudaStream_t stream);
 /* d_o = 0; d_d = dnorm_r / |d|^2 * d  (NDC rays: dists are scaled by |ray_dir|, batBase.py:63-65;
  * dnorm holds dL/d|d| * |d| from jt_render_bwd) or 0 when dnorm is NULL. */
 int jt_ray_init(const float* rays_d, const float* dnorm, int n_rays, float* d_o, float* d_d, cudaStream_t stream);
@@ -155,6 +158,9 @@ int jt_tc_selftest(int mode, const float* A, int lda, const float* B, int ldb, f
  * jt_head_tc_stage_bytes(n_max) bytes, 128-byte aligned, that receives the bf16 operand tiles
  * (components, encoded input, relu(h1), relu(h2)) jt_head_bwd_tc needs. */
 long long jt_head_tc_stage_bytes(int n_max);
+/* (unit-test harness: the monolithic first version of the tensor-core head, components read from HBM; the
+ * product path is jt_app_basis_fwd_tc + jt_head_mlp_fwd_tc. Kept because tests/test_gpu_tc.py stages the backward's
+ * operand tiles from arbitrary component rows with it.) */
 int jt_head_fwd_tc(int split, const float* comps, const int* aidx, const int* sidx, const float* rays_d,
                    int n_samples, int normalize_dir, const float* Wb, const float* W1, const float* b1,
                    const float* W2, const float* b2, const float* W3, const float* b3, const int* n_dev, int n_max,
@@ -223,10 +229,6 @@ int jt_render_bwd(const int* ray_off, int n_rays, const float* sigfeat, const fl
                   const float* trans, const int* app_of, const float* rgb, const float* rgb_pre,
                   const float* g_rgb, const float* g_acc, float density_shift, int act, float distance_scale,
                   int white_bg, int shade_act, float* dout, float* dsig, float* dnorm, cudaStream_t stream);
-/* dL/du per sample -> dL/d rays_o, dL/d rays_d (pts = o + d*t, normalize_coord). */
-int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* dsamp, const float* rays_d,
-               const float* dnorm, const float* h_inv, float* d_o, float* d_d, cudaStream_t stream);
-
 /* ---- K5: separable blur ------------------------------------------------ */
 /* BAT_VMSplit.convolute_plane / convolute_line (bateRF.py:8-39) on a channel-last
  * [H][W][C] array: replicate-padded cross-correlation with `h_taps` [ntaps] (HOST

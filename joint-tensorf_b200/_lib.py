@@ -19,7 +19,7 @@ SIGNATURES = {
     "jt_exclusive_scan": [_P, _P, _I, _P],
     "jt_vm_gather_fwd": [_I, _P, _P, _P, _P, _P, _I, _P, _P],
     "jt_vm_gather_bwd": [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P],
-    "jt_vm_scatter_rays": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P],
+    "jt_vm_scatter_rays": [_I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _I, _I, _P],
     "jt_ray_init": [_P, _P, _I, _P, _P, _P],
     "jt_gemm_nt": [_P, _I, _P, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
     "jt_gemm_tn": [_P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _P],
@@ -35,7 +35,6 @@ SIGNATURES = {
     "jt_alpha_fwd": [_P, _I, _P, _P, _P, _F, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_composite_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P],
     "jt_render_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _I, _I, _P, _P, _P, _P],
-    "jt_ray_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_blur_cl": [_P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P],
     "jt_blur_multi": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "jt_pose_rays_fwd": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P],

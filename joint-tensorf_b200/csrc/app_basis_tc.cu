@@ -84,19 +84,35 @@ __global__ void __launch_bounds__(GT, 2) app_basis_fwd_kernel(Factors F, const f
             const Tap tx = make_tap(u[mat0(i)], F.W[i]), ty = make_tap(u[mat1(i)], F.H[i]), tl = make_tap(u[vecm(i)], F.L[i]);
             const size_t C = CT / 3;
             const size_t r0 = (size_t)ty.i0 * F.W[i], r1 = (size_t)ty.i1 * F.W[i];
-            const size_t p00 = (r0 + tx.i0) * C + sub * 4, p10 = (r0 + tx.i1) * C + sub * 4;     // element offsets
-            const size_t p01 = (r1 + tx.i0) * C + sub * 4, p11 = (r1 + tx.i1) * C + sub * 4;
-            const size_t l0 = (size_t)tl.i0 * C + sub * 4, l1 = (size_t)tl.i1 * C + sub * 4;
-            const float* P = F.plane[i];
-            const float* Ln = F.line[i];
+            // fp32 taps: six live pointers + immediate offsets (the form the 64-register budget of this kernel was
+            // tuned for); bf16 taps: the same with 2-byte elements
+            const float* p00 = F.plane[i] + (r0 + tx.i0) * C + sub * 4;
+            const float* p10 = F.plane[i] + (r0 + tx.i1) * C + sub * 4;
+            const float* p01 = F.plane[i] + (r1 + tx.i0) * C + sub * 4;
+            const float* p11 = F.plane[i] + (r1 + tx.i1) * C + sub * 4;
+            const float* l0 = F.line[i] + (size_t)tl.i0 * C + sub * 4;
+            const float* l1 = F.line[i] + (size_t)tl.i1 * C + sub * 4;
+            const unsigned short* P16 = reinterpret_cast<const unsigned short*>(F.plane[i]);
+            const unsigned short* L16 = reinterpret_cast<const unsigned short*>(F.line[i]);
+            const unsigned short* h00 = P16 + (r0 + tx.i0) * C + sub * 4;
+            const unsigned short* h10 = P16 + (r0 + tx.i1) * C + sub * 4;
+            const unsigned short* h01 = P16 + (r1 + tx.i0) * C + sub * 4;
+            const unsigned short* h11 = P16 + (r1 + tx.i1) * C + sub * 4;
+            const unsigned short* hl0 = L16 + (size_t)tl.i0 * C + sub * 4;
+            const unsigned short* hl1 = L16 + (size_t)tl.i1 * C + sub * 4;
             const float w00 = tx.w0 * ty.w0, w10 = tx.w1 * ty.w0, w01 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float4 a, b, c, d, la, lb;
                 if (live) {
-                    a = ld_tap4<B16>(P, p00 + 16 * k); b = ld_tap4<B16>(P, p10 + 16 * k);
-                    c = ld_tap4<B16>(P, p01 + 16 * k); d = ld_tap4<B16>(P, p11 + 16 * k);
-                    la = ld_tap4<B16>(Ln, l0 + 16 * k); lb = ld_tap4<B16>(Ln, l1 + 16 * k);
+                    if (B16) {
+                        auto ld = [](const unsigned short* p) { return bf16x4_to_f4(__ldg(reinterpret_cast<const uint2*>(p))); };
+                        a = ld(h00 + 16 * k); b = ld(h10 + 16 * k); c = ld(h01 + 16 * k); d = ld(h11 + 16 * k);
+                        la = ld(hl0 + 16 * k); lb = ld(hl1 + 16 * k);
+                    } else {
+                        a = ldg4(p00 + 16 * k); b = ldg4(p10 + 16 * k); c = ldg4(p01 + 16 * k); d = ldg4(p11 + 16 * k);
+                        la = ldg4(l0 + 16 * k); lb = ldg4(l1 + 16 * k);
+                    }
                 } else {
                     a = b = c = d = la = lb = make_float4(0.f, 0.f, 0.f, 0.f);
                 }

@@ -143,8 +143,15 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const int* __restric
 //   dout[a]   = dL/d(pre-activation of the shading head)   (shade_act folds sigmoid / relu')
 //   dsig[j]   = dL/d sigma_feature
 //   dnorm[r]  = dL/d |ray_dir|   (NDC rays only: dists are scaled by the norm)
-// with S_j = sum_{i>j} dL/dw_i * w_i  (suffix sum) and
-//   dL/dalpha_j = dL/dw_j * T_j - S_j / (1 - alpha_j + 1e-10).
+// Autograd of raw2alpha (tensorBase.py:57-65) gives, with S_j = sum_{i>j} dL/dw_i * w_i,
+//   dL/dalpha_j = dL/dw_j * T_j - S_j / q_j,        q_j = 1 - alpha_j + 1e-10.
+// In a nearly opaque field with nearly constant colours the two terms cancel to ~1e-4 of their size, and their fp32
+// errors do not: T_j and the w_i inside S_j come from differently grouped products (a parallel scan here, a
+// sequential cumprod in the reference). The same quantity is therefore evaluated as
+//   dL/dalpha_j = T_j * (dL/dw_j - Y_j),   Y_j = S_j / (q_j T_j) = sum_{i>j} dL/dw_i alpha_i prod_{j<k<i} q_k,
+// where Y obeys the first-order recurrence Y_{j-1} = dL/dw_j alpha_j + q_j Y_j (a reverse scan of affine maps):
+// no transmittance enters the cancelling difference, only local factors do. Identical in exact arithmetic; in fp32
+// it is closer to the float64 result than the reference's own autograd is (tests/gpu_common.py slice_parity).
 __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__ off, int n_rays,
                                                          const float* __restrict__ sigfeat,
                                                          const float* __restrict__ dist,
@@ -191,68 +198,38 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
                     *reinterpret_cast<float4*>(dout + 4 * (size_t)a) = make_float4(d0, d1, d2, 0.f);
                 }
             }
-            float s = dw * w;                        // inclusive scan in reverse order
+            // per-sample factors of the recurrence (identity map for lanes past the ray's first sample)
+            float x = 0.f, sigma = 0.f, dd = 0.f, ex = 1.f, A = 0.f, Q = 1.f;
+            if (i < len) {
+                x = sf + shift;
+                sigma = density_act(x, act);
+                dd = dj * dscale;
+                ex = exp_neg(-sigma * dd);
+                const float alpha = 1.0f - ex;
+                Q = 1.0f - alpha + 1e-10f;
+                A = dw * alpha;
+            }
+            // inclusive scan, in reverse sample order, of the affine maps y -> A + Q y (composition:
+            // (A, Q) o (A', Q') = (A + Q A', Q Q')); lane i then maps the value behind the chunk to Y in front of sample j_i
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                float v = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += v;
+                const float a2 = __shfl_up_sync(0xffffffffu, A, o), q2 = __shfl_up_sync(0xffffffffu, Q, o);
+                if (lane >= o) { A = fmaf(Q, a2, A); Q *= q2; }
             }
-            float excl = __shfl_up_sync(0xffffffffu, s, 1);
-            if (lane == 0) excl = 0.f;
-            const float suffix = carry + excl;       // sum over samples behind j
+            const float zin = fmaf(Q, carry, A);     // Y in front of this lane's sample (includes it)
+            float ybehind = __shfl_up_sync(0xffffffffu, zin, 1);
+            if (lane == 0) ybehind = carry;          // Y_j: everything behind sample j
             if (i < len) {
-                const float x = sf + shift;
-                const float sigma = density_act(x, act);
-                const float dd = dj * dscale;
-                const float ex = exp_neg(-sigma * dd);
-                const float alpha = 1.0f - ex;
-                const float q = 1.0f - alpha + 1e-10f;
-                const float dalpha = dw * tj - suffix / q;
+                const float dalpha = tj * (dw - ybehind);
                 const float dsigma = dalpha * dd * ex;
                 dsig[j] = dsigma * density_act_grad(x, act);
                 dn += dalpha * sigma * ex * dd;      // d/d(norm) * norm
             }
-            carry += __shfl_sync(0xffffffffu, s, 31);
+            carry = __shfl_sync(0xffffffffu, zin, 31);
         }
         if (dnorm) {
             dn = warp_sum(dn);
             if (lane == 0) dnorm[r] = dn;
-        }
-    }
-}
-
-// per ray: dL/d rays_o = sum_j dL/du_j * inv;  dL/d rays_d = sum_j dL/du_j * inv * t_j
-// (+ NDC: dists = dz*|d|  ->  dL/d d += dnorm_r/|d| * d/|d|).
-__global__ void __launch_bounds__(256) ray_bwd_kernel(const int* __restrict__ off, int n_rays,
-                                                      const float4* __restrict__ samp,
-                                                      const float4* __restrict__ dsamp,
-                                                      const float* __restrict__ rays_d,
-                                                      const float* __restrict__ dnorm, float i0, float i1, float i2,
-                                                      float* __restrict__ d_o, float* __restrict__ d_d) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < n_rays; r += nwarps) {
-        const int b = off[r], e = off[r + 1];
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        for (int j = b + lane; j < e; j += 32) {
-            const float4 g = dsamp[j];
-            const float t = samp[j].w;
-            const float gx = g.x * i0, gy = g.y * i1, gz = g.z * i2;
-            o0 += gx; o1 += gy; o2 += gz;
-            d0 += gx * t; d1 += gy * t; d2 += gz * t;
-        }
-        o0 = warp_sum(o0); o1 = warp_sum(o1); o2 = warp_sum(o2);
-        d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
-        if (lane == 0) {
-            if (dnorm) {
-                const float x = rays_d[3 * r], y = rays_d[3 * r + 1], z = rays_d[3 * r + 2];
-                const float n2 = x * x + y * y + z * z;
-                const float k = n2 > 0.f ? dnorm[r] / n2 : 0.f;    // dnorm holds dL/dnorm * norm
-                d0 += k * x; d1 += k * y; d2 += k * z;
-            }
-            d_o[3 * r] = o0; d_o[3 * r + 1] = o1; d_o[3 * r + 2] = o2;
-            d_d[3 * r] = d0; d_d[3 * r + 1] = d1; d_d[3 * r + 2] = d2;
         }
     }
 }
@@ -321,18 +298,6 @@ extern "C" int jt_render_bwd(const int* ray_off, int n_rays, const float* sigfea
     render_bwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(ray_off, n_rays, sigfeat, dist, weight, trans, app_of, rgb,
                                                             rgb_pre, g_rgb, g_acc, density_shift, act, distance_scale,
                                                             white_bg, shade_act, dout, dsig, dnorm);
-    JT_RETURN_LAUNCH();
-}
-
-extern "C" int jt_ray_bwd(const int* ray_off, int n_rays, const float* samp, const float* dsamp,
-                          const float* rays_d, const float* dnorm, const float* h_inv, float* d_o, float* d_d,
-                          cudaStream_t stream) {
-    JT_CHECK_ARG(ray_off && samp && dsamp && rays_d && h_inv && d_o && d_d);
-    if (n_rays <= 0) return JT_OK;
-    g_launches += 1;
-    ray_bwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(ray_off, n_rays, reinterpret_cast<const float4*>(samp),
-                                                         reinterpret_cast<const float4*>(dsamp), rays_d, dnorm,
-                                                         h_inv[0], h_inv[1], h_inv[2], d_o, d_d);
     JT_RETURN_LAUNCH();
 }
 

@@ -20,6 +20,7 @@
 // dL/du array is written and no separate ray_bwd pass is needed.
 #include <limits.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "jt_common.cuh"
 #include "../../include/jt_vm.h"
 
@@ -72,6 +73,7 @@ struct ScatterArgs {
     int S;                  // samples per ray (sidx decoding)
     int seg;                // samples per walker segment (fixed), or
     int seg_target;         // > 0: persistent grid, segment length chosen in the kernel (see vm_scatter_walk_kernel)
+    int plane_mask;         // bit i: walk plane / line pair i in this launch (7 = all three)
 };
 
 // One walker = LW lanes; lane `sub` owns the NQ channel quads sub, sub + LW, ... of a plane
@@ -112,26 +114,27 @@ struct StepPos {          // tap position of one sample on one plane/line pair
 // gradients and the arithmetic stay fp32.
 template <bool APP, int NQ, int I, bool GB16, bool B16, int THR = SC_THREADS>
 __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, const int e1, const int q, const int qs,
-                                           int& ray, int& ray_end, RaySums& rs, unsigned char* __restrict__ sm) {
+                                           int& ray, int& ray_end, RaySums& rs,
+                                           typename std::conditional<B16, uint2, float4>::type* __restrict__ sm) {
+    using SlotT = typename std::conditional<B16, uint2, float4>::type;          // one staged channel quad
+    using ElemT = typename std::conditional<B16, unsigned short, float>::type;  // one factor element
     const Factors& F = A.F;
     constexpr int ax = I == 2 ? 1 : 0, ay = I == 0 ? 1 : 2, al = 2 - I;      // matMode / vecMode (tensorBase.py:405-406)
     const int W = F.W[I], H = F.H[I], L = F.L[I], C = F.C[I];
     if (q >= C) return;
-    constexpr int TS = B16 ? 8 : 16, ES = B16 ? 2 : 4;          // bytes per staged quad / per factor element
-    const unsigned char* __restrict__ P = reinterpret_cast<const unsigned char*>(F.plane[I]) + (size_t)q * ES;
-    const unsigned char* __restrict__ Ln = reinterpret_cast<const unsigned char*>(F.line[I]) + (size_t)q * ES;
+    const ElemT* __restrict__ P = reinterpret_cast<const ElemT*>(F.plane[I]) + q;
+    const ElemT* __restrict__ Ln = reinterpret_cast<const ElemT*>(F.line[I]) + q;
     float* __restrict__ GP = A.G.plane[I] + q;
     float* __restrict__ GL = A.G.line[I] + q;
     const float sclx = 0.5f * (float)(W - 1), scly = 0.5f * (float)(H - 1), scll = 0.5f * (float)(L - 1);
     // this lane's staging slots (float4 index = slot * SC_THREADS): plane buffer b, tap c, quad k -> (b*4 + c)*NQ + k;
     // line buffer b, tap c, quad k -> 8 NQ + (b*2 + c)*NQ + k
-    auto pslot = [&](int b, int c, int k) -> unsigned char* { return sm + ((b * 4 + c) * NQ + k) * (THR * TS); };
-    auto lslot = [&](int b, int c, int k) -> unsigned char* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * (THR * TS); };
-    auto rd = [&](const unsigned char* p) -> float4 {
-        if (B16) return bf16x4_to_f4(*reinterpret_cast<const uint2*>(p));
-        return *reinterpret_cast<const float4*>(p);
+    auto pslot = [&](int b, int c, int k) -> SlotT* { return sm + ((b * 4 + c) * NQ + k) * THR; };
+    auto lslot = [&](int b, int c, int k) -> SlotT* { return sm + (8 * NQ + (b * 2 + c) * NQ + k) * THR; };
+    auto rd = [&](const SlotT* p) -> float4 {
+        if constexpr (B16) return bf16x4_to_f4(*p); else return *p;
     };
-    auto cp = [&](unsigned char* dst, const unsigned char* src) { if (B16) cp_async8(dst, src); else cp_async16(dst, src); };
+    auto cp = [&](SlotT* dst, const ElemT* src) { if constexpr (B16) cp_async8(dst, src); else cp_async16(dst, src); };
 
     auto make_pos = [&](const float4 u4, const int sid) {
         const float u[3] = {u4.x, u4.y, u4.z};
@@ -158,13 +161,13 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) cp(pslot(b, c, k), P + (size_t)(o[c] + k * qs) * ES);
+            for (int k = 0; k < NQ; ++k) cp(pslot(b, c, k), P + o[c] + k * qs);
     };
     auto fetch_line = [&](int b, const unsigned o[2]) {
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) cp(lslot(b, c, k), Ln + (size_t)(o[c] + k * qs) * ES);
+            for (int k = 0; k < NQ; ++k) cp(lslot(b, c, k), Ln + o[c] + k * qs);
     };
     // upstream gradient of element e for this lane's quads: fetched raw one step ahead (the
     // conversion happens at use, so the load latency stays off the issue path)
@@ -346,13 +349,14 @@ __device__ __forceinline__ void walk_plane(const ScatterArgs& A, const int e0, c
 template <bool APP, int NQ, int MINB, bool GB16, int LWC, bool B16>
 __global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const ScatterArgs A, int LW_rt, int walkers_per_cta) {
     extern __shared__ __align__(16) unsigned char sc_smem[];   // 12 NQ slots x SC_THREADS quads (16 B fp32 / 8 B bf16)
+    using SlotT = typename std::conditional<B16, uint2, float4>::type;
     const int LW = LWC > 0 ? LWC : LW_rt;                // lanes per walker (compile-time strides when LWC > 0)
     const int n = A.n_dev ? *A.n_dev : A.n_fixed;
     const int wl = threadIdx.x / LW;                     // walker within the CTA
     const int q = (threadIdx.x - wl * LW) * 4;           // first channel of this lane's first quad
     const int qs = LW * 4;                               // channel stride between this lane's quads
     if (wl >= walkers_per_cta) return;
-    unsigned char* sm = sc_smem + threadIdx.x * (B16 ? 8 : 16);
+    SlotT* sm = reinterpret_cast<SlotT*>(sc_smem) + threadIdx.x;
     const int stride = gridDim.x * walkers_per_cta;      // walkers in the grid
     // Segment length. The grid is persistent (one wave of resident CTAs) and the units are dealt round-robin, so the
     // kernel takes ceil(units / walkers) rounds: a fixed length leaves up to a whole round idle at the end (measured
@@ -372,9 +376,9 @@ __global__ void __launch_bounds__(SC_THREADS, MINB) vm_scatter_walk_kernel(const
         RaySums rs;
 #pragma unroll
         for (int a = 0; a < 3; ++a) rs.o[a] = rs.d[a] = 0.f;
-        walk_plane<APP, NQ, 0, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
-        walk_plane<APP, NQ, 1, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
-        walk_plane<APP, NQ, 2, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        if (A.plane_mask & 1) walk_plane<APP, NQ, 0, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        if (A.plane_mask & 2) walk_plane<APP, NQ, 1, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
+        if (A.plane_mask & 4) walk_plane<APP, NQ, 2, GB16, B16>(A, e0, e1, q, qs, ray, ray_end, rs, sm);
     }
 }
 
@@ -385,8 +389,9 @@ using namespace jt;
 extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* const* h_factor_grads,
                                   const int* h_dims, const float* samp, const int* slot, const int* sidx,
                                   const int* n_dev, int n_max, const void* gin, int gin_bf16, int n_samples, const float* h_inv,
-                                  float* d_o, float* d_d, int max_ctas, cudaStream_t stream) {
+                                  float* d_o, float* d_d, int max_ctas, int plane_mask, cudaStream_t stream) {
     JT_CHECK_ARG(h_factors && h_factor_grads && h_dims && samp && sidx && gin && h_inv && d_o && d_d && n_samples > 0);
+    JT_CHECK_ARG(plane_mask > 0 && plane_mask <= 7);
     if (n_max <= 0) return JT_OK;
     ScatterArgs A;
     if (int rc = fill_factors(A.F, h_factors, h_dims)) return rc;
@@ -405,6 +410,7 @@ extern "C" int jt_vm_scatter_rays(int app, const void* const* h_factors, void* c
     A.d_o = d_o; A.d_d = d_d;
     for (int a = 0; a < 3; ++a) A.inv[a] = h_inv[a];
     A.S = n_samples;
+    A.plane_mask = plane_mask;
     // default: persistent grid, segment length derived in the kernel from the device-side count (target ~100
     // samples). JT_SCATTER_SEG=<n> (tuning) restores fixed n-sample segments on a non-persistent grid.
     static const int seg_env = getenv("JT_SCATTER_SEG") ? atoi(getenv("JT_SCATTER_SEG")) : 0;

@@ -193,13 +193,16 @@ def vm_gather_bwd(app, fs, gp, gl, samp, slot, n_dev, n_max, gin, dsamp, accumul
               "jt_vm_gather_bwd")
 
 
-def vm_scatter_rays(app, fs, gp, gl, samp, slot, sidx, n_dev, n_max, gin, n_samples, h_inv, d_o, d_d, max_ctas=0):
-    """Run-merged factor-gradient scatter + per-ray pose-path gradients (vm_scatter.cu)."""
+def vm_scatter_rays(app, fs, gp, gl, samp, slot, sidx, n_dev, n_max, gin, n_samples, h_inv, d_o, d_d, max_ctas=0,
+                    plane_mask=7):
+    """Run-merged factor-gradient scatter + per-ray pose-path gradients (vm_scatter.cu). plane_mask: which of the
+    three plane / line pairs this launch walks (7 = all)."""
     gptrs = ptrs([g.data_ptr() for g in gp] + [g.data_ptr() for g in gl])
     with TIMER.span("vm_app_bwd" if app else "vm_density_bwd"):
         check(_lib.lib().jt_vm_scatter_rays(int(app), fs.ptrs, gptrs, fs.dims, _p(samp), _p(slot), _p(sidx),
                                             _p(n_dev), int(n_max), _p(gin), int(gin.dtype == torch.bfloat16),
-                                            int(n_samples), h_inv, _p(d_o), _p(d_d), int(max_ctas), _stream()),
+                                            int(n_samples), h_inv, _p(d_o), _p(d_d), int(max_ctas), int(plane_mask),
+                                            _stream()),
               "jt_vm_scatter_rays")
 
 

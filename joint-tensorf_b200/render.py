@@ -266,6 +266,10 @@ class VMRender(torch.autograd.Function):
                         app_of=app_of, comps=comps, feat=feat, rgb=rgb, rgb_pre=rgb_pre, basis_w=basis_w, head=head,
                         a_count=a_count)
         ctx.n_head = len(head)
+        # version check only: the kernels read the parameters' storage directly, so an in-place update between
+        # forward and backward (an optimizer step, load_state_dict) must raise as it does for the reference's ATen
+        # nodes instead of silently differentiating the new values
+        ctx.save_for_backward(*tensors)
         ctx.mark_non_differentiable(depth)
         VMRender.last_counts = (comp.count, a_count)      # device scalars V, A (diagnostics / bench)
         return rgb_map, depth, opacity
@@ -274,6 +278,11 @@ class VMRender(torch.autograd.Function):
     def backward(ctx, g_rgb, g_depth, g_acc):
         lib = _lib.lib()
         cfg, comp, dfs, afs, ws, b = ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws, ctx.bufs
+        _ = ctx.saved_tensors                                 # raises if a parameter was modified in place since forward
+        if ws.get("consumed"):
+            raise _lib.JtError("second backward through the same render call: the strict-fp32 MLP head reuses its "
+                               "encoded-input buffer for the input gradient (2.6 GB at 4096 x 1000 samples); call "
+                               "forward again, or use head_precision='tc' / SH shading, whose backward is re-entrant")
         dev = g_rgb.device
         N, cap = comp.n_rays, comp.cap
         F = cfg.app_dim
@@ -337,21 +346,35 @@ class VMRender(torch.autograd.Function):
         else:
             dfeat, hg = _Head.backward(cfg, ws, dout, b["feat"], ldf, b["aidx"], comp.sidx, b["rays_d"],
                                        b["a_count"], cap, b["head"], dev)
+            if cfg.shading != "SH":
+                ws["consumed"] = True
             for dst, src in zip(head_grads, hg):
                 dst.copy_(src)
             ops.gemm_tn(dfeat, ldf, b["comps"], afs.ctot, b["a_count"], cap, F, afs.ctot, g_basis, afs.ctot, None,
                         name="basis_bwd_w")
             ops.gemm_nt(dfeat, ldf, b["basis_w"], afs.ctot, 1, None, dcomps, afs.ctot, None, 0, b["a_count"], cap,
                         afs.ctot, F, 0, name="basis_bwd_x")
-        ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
-                            cfg.n_samples, cfg.h_inv, d_o, d_d)
-        if sync is not None:
-            sync.on_app_grads(flat[:n_app])          # 3/4 of the bytes: reduced while the density scatter runs
-        # data parallel: the appearance all-reduce runs next to this kernel -> non-persistent grid (80-sample segments)
-        ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
-                            cfg.h_inv, d_o, d_d, max_ctas=(-80 if sync is not None else 0))
-        if sync is not None:
-            # the current stream waits here for both reductions: whatever autograd does with the views next (hand
+        if sync is None:
+            ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
+                                cfg.n_samples, cfg.h_inv, d_o, d_d)
+            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+                                cfg.h_inv, d_o, d_d)
+        else:
+            # data parallel: the appearance planes are walked one launch per plane, and each plane's gradients are
+            # all-reduced (NCCL's stream) while the next launches run: [plane 0] [plane 1] [plane 2 + the three
+            # lines] [density factors + basis_mat + head]; only the last ~1/4 of the bucket can be exposed. Fixed
+            # 80-sample segments on a non-persistent grid: the collectives' CTAs can only get onto an SM when scatter
+            # CTAs retire (a persistent wave holds every SM's registers until its kernel ends).
+            o = 0
+            for i in range(3):
+                ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
+                                    cfg.n_samples, cfg.h_inv, d_o, d_d, max_ctas=-80, plane_mask=1 << i)
+                end = o + sizes[i] if i < 2 else n_app
+                sync.on_app_grads(flat[o:end])
+                o = end
+            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+                                cfg.h_inv, d_o, d_d, max_ctas=-80)
+            # the current stream waits here for all reductions: whatever autograd does with the views next (hand
             # them to p.grad, clone them, feed the adjoint blur) sees the cross-rank sums
             sync.on_rest(flat[n_app:])
 

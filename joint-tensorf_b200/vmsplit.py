@@ -574,6 +574,9 @@ class B200_VMSplit(torch.nn.Module):
         for f in _OPT_FLAGS:
             if getattr(arch, f, False):
                 raise _lib.JtError(f"opt.arch.{f}=True is not implemented by the B200 path (False in all reference configs)")
+        if getattr(getattr(opt, "nerf", None), "bbox_cycle_xy", False):
+            raise _lib.JtError("opt.nerf.bbox_cycle_xy=True (tensorBase.py:581-608: wrapped x/y sampling) is not "
+                               "implemented by the B200 path (absent from every reference config)")
         sh = arch.shading
         if not (sh.detach_viewdirs and sh.detach_xyz):
             raise _lib.JtError("the B200 path implements detach_viewdirs/detach_xyz = True (all reference configs)")

@@ -259,12 +259,25 @@ def test_full_size_cfg2_properties(head, wl, blur):
                                 **bkw)
     assert bool(((rgb >= 0) & (rgb <= 1)).all()) and bool(((acc >= -1e-5) & (acc <= 1 + 1e-4)).all())
     assert torch.isfinite(depth).all()
-    # (3) linearity of the backward pass in the upstream gradient
+    # (3) linearity of the backward pass in the upstream gradient (a fresh forward per gradient: the strict-fp32 MLP
+    # head's backward is single-use, and the tensor-core / SH paths are exercised re-entrantly)
     w1, w2 = torch.rand_like(rgb), torch.rand_like(rgb)
     params = [m.density_plane[0], m.app_line[1], m.basis_mat.weight]
-    ga = torch.autograd.grad((rgb * w1).sum(), params + [og], retain_graph=True)
-    gb = torch.autograd.grad((rgb * w2).sum(), params + [og], retain_graph=True)
-    gc = torch.autograd.grad((rgb * (w1 + 2 * w2)).sum(), params + [og])
+    reentrant = head == "tc" or shading == "SH"
+
+    def grads_for(w, out=None, keep=False):
+        if out is None:
+            out = m.forward(default_opt(shading), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit, **bkw)[0]
+        return torch.autograd.grad((out * w).sum(), params + [og], retain_graph=keep)
+
+    if reentrant:
+        ga, gb, gc = grads_for(w1, rgb, True), grads_for(w2, rgb, True), grads_for(w1 + 2 * w2, rgb)
+    else:
+        ga, gb, gc = grads_for(w1), grads_for(w2), grads_for(w1 + 2 * w2)
+        with pytest.raises(jt._lib.JtError):             # the single-use guard
+            out = m.forward(default_opt(shading), og, dg, white_bg=True, is_train=True, N_samples=S, jitter=jit, **bkw)[0]
+            torch.autograd.grad(out.sum(), [og], retain_graph=True)
+            torch.autograd.grad(out.sum(), [og])
     for a, b, c in zip(ga, gb, gc):
         assert rel_err(a + 2 * b, c) <= max(gtol, 1e-3)          # self-consistency (atomics reorder the sums)
     del rgb, depth, acc, ga, gb, gc

@@ -208,3 +208,23 @@ def test_workload_descriptions_name_the_baseline_config():
     s = jt.synth.describe("cfg2_sh", 4096)
     assert "300^3" in s and "3x16" in s and "3x48" in s and "app_dim 27" in s and "SH" in s and "4096 rays/GPU" in s
     assert "MLP_Fea" in jt.synth.describe("cfg2") and "617x687x617" in jt.synth.describe("cfg4")
+
+
+def test_opt_fixtures_match_the_reference_options_py():
+    """tests/golden/opt_*.json (used by tests/test_gpu_reference_callsite.py on the GPU box) are exactly what the
+    reference's options.py builds from its shipped YAMLs; re-derived here whenever /root/reference is mounted."""
+    import json
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    import make_opt_fixture as mof
+    import ref_loader
+    for y, mdl in mof.YAMLS.items():
+        path = os.path.join(gold, f"opt_{y}.json")
+        assert os.path.exists(path), path
+        have = json.load(open(path))
+        assert have["arch"]["tensorf"]["model"] == "BAT_VMSplit" and "c2f_kernel_size" in have
+        if ref_loader.available():
+            want = json.loads(json.dumps(mof.build(y, mdl), sort_keys=True, default=str))
+            assert want == have, y

@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="N > 1: cap the CTAs NCCL may use (NCCL_MAX_CTAS) so the collectives leave SMs to the kernels "
                          "they overlap with (0 = NCCL's default)")
+    ap.add_argument("--sync-per-plane", action="store_true", help="N > 1: one scatter launch + all-reduce per appearance plane")
+    ap.add_argument("--sync-reserve-sms", type=int, default=0,
+                    help="N > 1: SMs the density scatter leaves free for the all-reduce running next to it")
     ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"],
                     help="VM factor storage the gathers read (fp32 master parameters either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -506,7 +509,8 @@ def own_arm(args):
     params = [p for p in model.parameters()] + [se3_refine]
     # data parallel: the render node's backward reduces its flat gradient bucket across ranks itself (appearance
     # part overlapped with the density scatter); the loss carries the 1/world factor, so the sums are means
-    sync = parallel.OverlappedGradSync().attach(model, [se3_refine]) if world > 1 else None
+    sync = (parallel.OverlappedGradSync(per_plane=args.sync_per_plane, reserve_sms=args.sync_reserve_sms)
+            .attach(model, [se3_refine]) if world > 1 else None)
     inv_world = 1.0 / world
 
     def make_step(model, opt, params):
@@ -546,6 +550,12 @@ def own_arm(args):
         # every later step; nothing inside an event pair changes.
         for _ in range(6):
             flush.fill_(1.0)
+        if world > 1:
+            # device-side rendezvous in front of the first timed step: the hosts reach this point a few ms apart
+            # (thread start-up, GC), and without it rank 0's first gradient all-reduce waits for the last rank to
+            # arrive -- 6.85 ms instead of 3.2 ms for the first of the 20 steps in SCALE_r01 at N = 8. The hosts keep
+            # queueing the first step while the streams wait here, as they do in front of every later step.
+            dist.all_reduce(tok)
         for _ in range(k):
             flush.fill_(1.0)                                           # evict L2 between steps (untimed)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -210,17 +210,22 @@ int jt_sh_bwd_tc(const float* dout, const float* featdir, int ldf, const float* 
  * (tensorBase.py:57-65) over the compacted samples of each ray, then the app_mask
  * selection weight > thres (batBase.py:127) compacted: app_off [N+1], aidx [A] ->
  * sample slot, app_of [V] -> appearance slot or -1. Also per ray acc = sum w and
- * wz = sum w*t. */
+ * wz = sum w*t.
+ * app_cap bounds the appearance list (capacity of the caller's appearance-stage buffers; N*S = unbounded):
+ * entries past it are dropped (app_of = -1), and app_used (device int[2], may be NULL) receives
+ * {min(A, app_cap), A > app_cap}; app_off[N] keeps the true A. The appearance-stage kernels take app_used as
+ * their device-side count, so an under-estimated capacity degrades that call (flagged) instead of overrunning. */
 int jt_alpha_fwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist, const float* samp,
                  float density_shift, int act, float distance_scale, float thres, float* weight, float* trans,
-                 float* acc, float* wz, int* app_cnt, int* app_off, int* aidx, int* app_of, cudaStream_t stream);
+                 float* acc, float* wz, int* app_cnt, int* app_off, int* aidx, int* app_of, int app_cap,
+                 int* app_used, cudaStream_t stream);
 /* batBase.py:142-165: rgb_map = clamp(sum w*rgb (+ 1-acc if white_bg), 0, 1);
  * depth = sum w*t + (1-acc)*ray_dir_z + depth_bias (depth_bias = -near + 0.05);
  * opacity = acc. rgb_pre keeps the un-clamped colour for the backward pass.
  * Per-sample colours `rgb` and their gradients `dout` are [A][4] (xyz used). */
 int jt_composite_fwd(const int* app_off, int n_rays, const int* aidx, const float* weight, const float* rgb,
                      const float* acc, const float* wz, const float* rays_d, int white_bg, float depth_bias,
-                     float* rgb_pre, float* rgb_map, float* depth, float* opacity, cudaStream_t stream);
+                     float* rgb_pre, float* rgb_map, float* depth, float* opacity, int app_cap, cudaStream_t stream);
 /* autograd of composite + raw2alpha + feature2density as one reverse scan per ray:
  * (g_rgb [N,3], g_acc [N] or NULL) -> dout [A,3] (gradient at the shading head's
  * pre-activation; shade_act 0 none, 1 sigmoid, 2 relu), dsig [V] (gradient of the

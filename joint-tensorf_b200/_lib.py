@@ -32,8 +32,8 @@ SIGNATURES = {
     "jt_head_bwd_tc": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "jt_app_basis_sh_fwd_tc": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P],
     "jt_sh_bwd_tc": [_P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P],
-    "jt_alpha_fwd": [_P, _I, _P, _P, _P, _F, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "jt_composite_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P],
+    "jt_alpha_fwd": [_P, _I, _P, _P, _P, _F, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "jt_composite_fwd": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _P],
     "jt_render_bwd": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _F, _I, _I, _P, _P, _P, _P],
     "jt_blur_cl": [_P, _P, _P, _I, _I, _I, _P, _I, _I, _I, _P],
     "jt_blur_multi": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],

@@ -76,12 +76,21 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
 
 // ------------------------------------------------------------------ forward, pass B
 // appearance compaction: aidx[a] = sample slot j, app_of[j] = a (or -1).
+// app_cap bounds the appearance list: entries a >= app_cap are dropped (app_of = -1, nothing written to aidx) and
+// app_used = {min(A, app_cap), A > app_cap} tells the caller -- every later kernel of the appearance stage takes
+// app_used[0] as its device-side count, so buffers sized app_cap are never overrun.
 __global__ void __launch_bounds__(256) app_fill_kernel(const int* __restrict__ off, const int* __restrict__ aoff,
                                                        int n_rays, const float* __restrict__ weight, float thres,
-                                                       int* __restrict__ aidx, int* __restrict__ app_of) {
+                                                       int* __restrict__ aidx, int* __restrict__ app_of, int app_cap,
+                                                       int* __restrict__ app_used) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (app_used && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int total = aoff[n_rays];
+        app_used[0] = min(total, app_cap);
+        app_used[1] = total > app_cap ? 1 : 0;
+    }
     for (int r = warp; r < n_rays; r += nwarps) {
         const int b = off[r], e = off[r + 1];
         int base = aoff[r];
@@ -91,8 +100,9 @@ __global__ void __launch_bounds__(256) app_fill_kernel(const int* __restrict__ o
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (j < e) {
                 int a = ok ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+                if (a >= app_cap) a = -1;
                 app_of[j] = a;
-                if (ok) aidx[a] = j;
+                if (a >= 0) aidx[a] = j;
             }
             base += __popc(m);
         }
@@ -110,12 +120,12 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const int* __restric
                                                             const float* __restrict__ rays_d, int white_bg,
                                                             float depth_bias, float* __restrict__ rgb_pre,
                                                             float* __restrict__ rgb_map, float* __restrict__ depth,
-                                                            float* __restrict__ opacity) {
+                                                            float* __restrict__ opacity, int app_cap) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp; r < n_rays; r += nwarps) {
-        const int b = aoff[r], e = aoff[r + 1];
+        const int b = min(aoff[r], app_cap), e = min(aoff[r + 1], app_cap);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         for (int a = b + lane; a < e; a += 32) {
             const float w = weight[aidx[a]];
@@ -261,9 +271,10 @@ using namespace jt;
 extern "C" int jt_alpha_fwd(const int* ray_off, int n_rays, const float* sigfeat, const float* dist,
                             const float* samp, float density_shift, int act, float distance_scale, float thres,
                             float* weight, float* trans, float* acc, float* wz, int* app_cnt, int* app_off,
-                            int* aidx, int* app_of, cudaStream_t stream) {
+                            int* aidx, int* app_of, int app_cap, int* app_used, cudaStream_t stream) {
     JT_CHECK_ARG(ray_off && sigfeat && dist && samp && weight && trans && acc && wz && app_cnt && app_off && aidx && app_of);
     JT_CHECK_ARG(act == 0 || act == 1);
+    JT_CHECK_ARG(app_cap > 0);
     if (n_rays <= 0) return JT_OK;
     int grid = ray_grid(n_rays);
     g_launches += 2;
@@ -271,19 +282,20 @@ extern "C" int jt_alpha_fwd(const int* ray_off, int n_rays, const float* sigfeat
                                                density_shift, act, distance_scale, thres, weight, trans, acc, wz,
                                                app_cnt);
     if (int rc = jt_exclusive_scan(app_cnt, app_off, n_rays, stream)) return rc;
-    app_fill_kernel<<<grid, 256, 0, stream>>>(ray_off, app_off, n_rays, weight, thres, aidx, app_of);
+    app_fill_kernel<<<grid, 256, 0, stream>>>(ray_off, app_off, n_rays, weight, thres, aidx, app_of, app_cap, app_used);
     JT_RETURN_LAUNCH();
 }
 
 extern "C" int jt_composite_fwd(const int* app_off, int n_rays, const int* aidx, const float* weight,
                                 const float* rgb, const float* acc, const float* wz, const float* rays_d,
                                 int white_bg, float depth_bias, float* rgb_pre, float* rgb_map, float* depth,
-                                float* opacity, cudaStream_t stream) {
+                                float* opacity, int app_cap, cudaStream_t stream) {
     JT_CHECK_ARG(app_off && aidx && weight && rgb && acc && wz && rays_d && rgb_pre && rgb_map && depth && opacity);
     if (n_rays <= 0) return JT_OK;
     g_launches += 1;
     composite_fwd_kernel<<<ray_grid(n_rays), 256, 0, stream>>>(app_off, n_rays, aidx, weight, rgb, acc, wz, rays_d,
-                                                               white_bg, depth_bias, rgb_pre, rgb_map, depth, opacity);
+                                                               white_bg, depth_bias, rgb_pre, rgb_map, depth, opacity,
+                                                               app_cap > 0 ? app_cap : 2147483647);
     JT_RETURN_LAUNCH();
 }
 

@@ -85,11 +85,13 @@ class OverlappedGradSync:
         seeded differently.
     World size 1: every call is a no-op."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, per_plane=False, reserve_sms=0):
         self.group = group
         self.works = []
         self.bytes = 0
         self.enabled = True
+        self.per_plane = per_plane        # one scatter launch + all-reduce per appearance plane (render.py)
+        self.reserve_sms = reserve_sms    # SMs the density scatter leaves to the collective running next to it
 
     def _active(self):
         return self.enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1

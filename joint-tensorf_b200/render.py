@@ -57,6 +57,9 @@ class RenderCfg:
         self.storage = "fp32"       # "bf16": the kernels gather from a bf16 copy of the factors (fp32 masters / gradients)
         self.store_cache = (None, None)
         self.bf16_backward_taps = False
+        self.app_cap = None         # capacity of the appearance-stage buffers for training calls (None: N*S)
+        self.app_monitor = None     # callable(a_total_dev, app_used_dev, n_rays): B200_VMSplit's capacity tracker
+        self.infer_exact_alloc = True   # no-grad calls read A on the host and allocate exactly
         self.__dict__.update(kw)
 
 
@@ -204,18 +207,32 @@ class VMRender(torch.autograd.Function):
         app_off = torch.zeros((N + 1,), device=dev, dtype=torch.int32)
         aidx = torch.empty((cap,), device=dev, dtype=torch.int32)
         app_of = torch.empty((cap,), device=dev, dtype=torch.int32)
+        # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), and grad mode is always
+        # off inside Function.forward: the caller records it in cfg.grad_enabled. Without this test every
+        # full-frame render ran the training forward (staging tiles written for a backward that never comes).
+        train = cfg.grad_enabled and any(ctx.needs_input_grad)
+        # Memory model of the appearance stage: the number of appearance samples A only exists on
+        # the device. Training sizes the appearance-stage buffers (features, staged operand tiles, dcomps) to
+        # `acap` = cfg.app_cap, a host-side bound kept by B200_VMSplit from the counts of earlier steps (read back
+        # asynchronously; N*S when there is no history) -- jt_alpha_fwd clamps the list to it and raises a device flag
+        # that the module checks at its next call. No-grad calls read A on the host (the reference synchronises at
+        # the same place: boolean-mask indexing, batBase.py:128) and allocate exactly.
+        acap = cap if (cfg.app_cap is None or not train) else max(1, min(cap, int(cfg.app_cap)))
+        app_used = torch.zeros((2,), device=dev, dtype=torch.int32)
         with TIMER.span("alpha_fwd"):
             check(lib.jt_alpha_fwd(_p(comp.ray_off), N, _p(sigfeat), _p(comp.dist), _p(comp.samp),
                                    float(cfg.density_shift), cfg.act, float(cfg.distance_scale), float(cfg.thres),
                                    _p(weight), _p(trans), _p(acc), _p(wz), _p(app_cnt), _p(app_off), _p(aidx),
-                                   _p(app_of), _stream()), "jt_alpha_fwd")
-        a_count = app_off[N:N + 1]
+                                   _p(app_of), int(acap), _p(app_used), _stream()), "jt_alpha_fwd")
+        a_count = app_used[0:1]                   # min(A, acap); the true A stays in app_off[N]
+        if not train and cfg.infer_exact_alloc:
+            acap = max(int(a_count.item()), 1)
+        cap_v, cap = cap, acap                    # from here on `cap` sizes the APPEARANCE stage; cap_v = N*S
 
         ws = {}
         comps = None
         if cfg.head == "tc" and cfg.shading == "MLP_Fea_WeakView":
             tc_supported(cfg, afs, raise_if_not=True)
-            train = cfg.grad_enabled and any(ctx.needs_input_grad)
             comps = torch.empty((cap, afs.ctot), device=dev)
             ops.vm_gather_fwd(1, afs, comp.samp, aidx, a_count, cap, comps)
             feat = torch.empty((cap, 32), device=dev)             # feat 0..19 | 0 | view dir 28..30 | 0
@@ -227,10 +244,6 @@ class VMRender(torch.autograd.Function):
         elif cfg.head == "tc":
             tc_supported(cfg, afs, raise_if_not=True)
             rgb = torch.empty((cap, 4), device=dev)
-            # needs_input_grad mirrors requires_grad of the inputs even under torch.no_grad(), and grad mode is always
-            # off inside Function.forward: the caller records it in cfg.grad_enabled. Without this test every
-            # full-frame render ran the training forward (staging tiles written for a backward that never comes).
-            train = cfg.grad_enabled and any(ctx.needs_input_grad)
             feat = torch.empty((cap, 32), device=dev)             # feat 0..26 | 0 | view dir 28..30 | 0
             ws["stage"] = ops.head_tc_stage(cap, dev) if train else None
             if cfg.shading == "SH":
@@ -259,19 +272,23 @@ class VMRender(torch.autograd.Function):
         with TIMER.span("composite_fwd"):
             check(lib.jt_composite_fwd(_p(app_off), N, _p(aidx), _p(weight), _p(rgb), _p(acc), _p(wz), _p(rays_d),
                                        int(cfg.white_bg), float(cfg.depth_bias), _p(rgb_pre), _p(rgb_map),
-                                       _p(depth), _p(opacity), _stream()), "jt_composite_fwd")
+                                       _p(depth), _p(opacity), int(cap), _stream()), "jt_composite_fwd")
 
         ctx.cfg, ctx.comp, ctx.dfs, ctx.afs, ctx.ws = cfg, comp, dfs32, afs32, ws
         ctx.bufs = dict(rays_d=rays_d, sigfeat=sigfeat, weight=weight, trans=trans, app_off=app_off, aidx=aidx,
                         app_of=app_of, comps=comps, feat=feat, rgb=rgb, rgb_pre=rgb_pre, basis_w=basis_w, head=head,
                         a_count=a_count)
         ctx.n_head = len(head)
+        ctx.acap = cap
         # version check only: the kernels read the parameters' storage directly, so an in-place update between
         # forward and backward (an optimizer step, load_state_dict) must raise as it does for the reference's ATen
         # nodes instead of silently differentiating the new values
         ctx.save_for_backward(*tensors)
         ctx.mark_non_differentiable(depth)
-        VMRender.last_counts = (comp.count, a_count)      # device scalars V, A (diagnostics / bench)
+        VMRender.last_counts = (comp.count, app_off[N:N + 1])      # device scalars V, A (diagnostics / bench)
+        VMRender.last_app_used = app_used                           # {min(A, capacity), overflow flag}
+        if cfg.app_monitor is not None and train:
+            cfg.app_monitor(app_off[N:N + 1], app_used, N)
         return rgb_map, depth, opacity
 
     @staticmethod
@@ -284,7 +301,7 @@ class VMRender(torch.autograd.Function):
                                "encoded-input buffer for the input gradient (2.6 GB at 4096 x 1000 samples); call "
                                "forward again, or use head_precision='tc' / SH shading, whose backward is re-entrant")
         dev = g_rgb.device
-        N, cap = comp.n_rays, comp.cap
+        N, cap_v, cap = comp.n_rays, comp.cap, ctx.acap       # cap: appearance-stage capacity, cap_v = N*S
         F = cfg.app_dim
         ldf = _r4(F)
         g_rgb = g_rgb.contiguous().float()
@@ -292,7 +309,7 @@ class VMRender(torch.autograd.Function):
         shade_act = 2 if cfg.shading == "SH" else 1
 
         dout = torch.empty((cap, 4), device=dev)
-        dsig = torch.empty((cap,), device=dev)
+        dsig = torch.empty((cap_v,), device=dev)
         dnorm = torch.empty((N,), device=dev) if cfg.ndc else None
         with TIMER.span("render_bwd"):
             check(lib.jt_render_bwd(_p(comp.ray_off), N, _p(b["sigfeat"]), _p(comp.dist), _p(b["weight"]),
@@ -302,7 +319,9 @@ class VMRender(torch.autograd.Function):
                   "jt_render_bwd")
 
         if VMRender.debug_capture is not None:            # diagnostics (scripts/debug_cfg4_grad.py): per-sample gradients
-            VMRender.debug_capture.update(dsig=dsig.clone(), dout=dout.clone(), count=comp.count.clone())
+            VMRender.debug_capture.update(dsig=dsig.clone(), dout=dout.clone(), count=comp.count.clone(),
+                                          weight=b["weight"].clone(), trans=b["trans"].clone(), rgb=b["rgb"].clone(),
+                                          sigfeat=b["sigfeat"].clone(), a_count=b["a_count"].clone())
 
         # One flat zero-filled bucket for every gradient this node produces (one memset; also the unit the
         # data-parallel all-reduce works on): [app planes, app lines | density planes, density lines | basis, head].
@@ -357,14 +376,13 @@ class VMRender(torch.autograd.Function):
         if sync is None:
             ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
                                 cfg.n_samples, cfg.h_inv, d_o, d_d)
-            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap_v, dsig, cfg.n_samples,
                                 cfg.h_inv, d_o, d_d)
-        else:
-            # data parallel: the appearance planes are walked one launch per plane, and each plane's gradients are
-            # all-reduced (NCCL's stream) while the next launches run: [plane 0] [plane 1] [plane 2 + the three
-            # lines] [density factors + basis_mat + head]; only the last ~1/4 of the bucket can be exposed. Fixed
-            # 80-sample segments on a non-persistent grid: the collectives' CTAs can only get onto an SM when scatter
-            # CTAs retire (a persistent wave holds every SM's registers until its kernel ends).
+        elif getattr(sync, "per_plane", False):
+            # variant (OverlappedGradSync(per_plane=True)): the appearance planes are walked one launch per plane and
+            # each plane's gradients are all-reduced while the next launches run -- [plane 0] [plane 1] [plane 2 + the
+            # three lines] [density + basis_mat + head]. Measured at N = 2 (profiles/r02e): the exposed wait halves
+            # (0.21 -> 0.12 ms) but the non-persistent per-plane launches cost 0.11 ms more than they save.
             o = 0
             for i in range(3):
                 ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
@@ -372,9 +390,23 @@ class VMRender(torch.autograd.Function):
                 end = o + sizes[i] if i < 2 else n_app
                 sync.on_app_grads(flat[o:end])
                 o = end
-            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap, dsig, cfg.n_samples,
+            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap_v, dsig, cfg.n_samples,
                                 cfg.h_inv, d_o, d_d, max_ctas=-80)
-            # the current stream waits here for all reductions: whatever autograd does with the views next (hand
+            sync.on_rest(flat[n_app:])
+        else:
+            # data parallel: the appearance part of the bucket (3/4 of the bytes) is all-reduced on NCCL's stream while
+            # the density scatter runs. The collective's CTAs can only get onto an SM when scatter CTAs retire (a
+            # persistent wave holds every SM's registers until its kernel ends): the density scatter either runs
+            # fixed 80-sample segments on a non-persistent grid, or (sync.reserve_sms > 0) a persistent wave that
+            # leaves that many SMs to the collective.
+            ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
+                                cfg.n_samples, cfg.h_inv, d_o, d_d)
+            sync.on_app_grads(flat[:n_app])
+            reserve = int(getattr(sync, "reserve_sms", 0))
+            resident = 4 if dfs.C[0] == 16 else 3
+            ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap_v, dsig, cfg.n_samples,
+                                cfg.h_inv, d_o, d_d, max_ctas=((148 - reserve) * resident if reserve > 0 else -80))
+            # the current stream waits here for both reductions: whatever autograd does with the views next (hand
             # them to p.grad, clone them, feed the adjoint blur) sees the cross-rank sums
             sync.on_rest(flat[n_app:])
 

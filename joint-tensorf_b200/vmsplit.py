@@ -93,6 +93,61 @@ class AlphaGridMask(torch.nn.Module):
         return (xyz_sampled - self.aabb[0]) * self.invgridSize - 1
 
 
+# ------------------------------------------------------------------ appearance-stage capacity (memory model)
+class AppCapacityTracker:
+    """Host-side bound on the number of appearance samples of a training call.
+
+    A (samples whose weight passes rayMarch_weight_thres) only exists on the device, and the appearance stage is
+    where the large per-sample buffers live (staged operand tiles: 1.26 KB per sample with the MLP_Fea head). The
+    tracker receives A of every training call through an asynchronous device->pinned-host copy (no
+    synchronisation: the value is read when its event has completed, typically one or two calls later), keeps a
+    slowly decaying maximum of A per ray, and after `warm` observations sizes the stage to
+    `margin * max_per_ray * n_rays + floor` (at most N*S). jt_alpha_fwd clamps the list to that capacity and raises
+    a device flag; if the flag ever comes back set, the next forward raises JtError -- the flagged call rendered
+    with a truncated appearance list -- and the capacity returns to N*S until the history is rebuilt."""
+
+    def __init__(self, margin=2.0, floor=65536, warm=8, decay=0.995):
+        self.margin, self.floor, self.warm, self.decay = margin, floor, warm, decay
+        self.reset()
+
+    def reset(self):
+        self.max_per_ray, self.seen, self.pending, self.overflow = 0.0, 0, [], None
+        self._pool = getattr(self, "_pool", [])
+
+    def submit(self, a_total, app_used, n_rays):
+        host = self._pool.pop() if self._pool else torch.empty((3,), dtype=torch.int32).pin_memory()
+        host[0:1].copy_(a_total, non_blocking=True)
+        host[1:3].copy_(app_used, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((ev, host, int(n_rays)))
+
+    def poll(self):
+        while self.pending and self.pending[0][0].query():
+            ev, host, n = self.pending.pop(0)
+            a, used, ovf = (int(v) for v in host.tolist())
+            if ovf:
+                self.overflow = (a, used)
+            self.max_per_ray = max(self.max_per_ray * self.decay, a / max(n, 1))
+            self.seen += 1
+            self._pool.append(host)
+        if len(self.pending) > 64:                     # nobody polls fast enough: drop the oldest
+            self.pending = self.pending[-64:]
+
+    def capacity(self, n_rays, cap):
+        self.poll()
+        if self.overflow is not None:
+            a, used = self.overflow
+            self.reset()
+            raise _lib.JtError(
+                f"appearance capacity exceeded in an earlier training call: {a} appearance samples, buffers sized for "
+                f"{used}; that call composited a truncated sample list. The capacity is back to N*S; set "
+                "B200_VMSplit.app_capacity = None to keep it there (INTEGRATION.md, memory model).")
+        if self.seen < self.warm:
+            return None
+        return min(int(cap), int(self.margin * self.max_per_ray * n_rays) + self.floor)
+
+
 # ------------------------------------------------------------------ shading heads (parameter containers)
 class MLPRender_Fea(torch.nn.Module):
     """Parameter layout of reference MLPRender_Fea (tensorBase.py:101-114): mlp.{0,2,4}."""
@@ -149,6 +204,10 @@ class B200_VMSplit(torch.nn.Module):
         # dtype=torch.bfloat16 at construction or by setting `factor_storage = "bf16"` afterwards.
         self.factor_storage = "bf16" if dtype == torch.bfloat16 else "fp32"
         self._store_cache = ({}, {})          # bf16 copies of the density / appearance factors (no-blur calls)
+        # "auto": training calls size the appearance-stage buffers from the appearance counts of earlier calls
+        # (AppCapacityTracker); None: always N*S. No-grad calls read the count on the host and allocate exactly.
+        self.app_capacity = "auto"
+        self._app_tracker = AppCapacityTracker()
         self.dtype = torch.float32
         self.alphaMask = alphaMask
         self.matMode = [list(m) for m in MAT_MODE]
@@ -549,6 +608,12 @@ class B200_VMSplit(torch.nn.Module):
         if self.factor_storage not in ("fp32", "bf16"):
             raise _lib.JtError(f"factor_storage {self.factor_storage!r}: expected 'fp32' or 'bf16'")
         cfg.storage = self.factor_storage
+        if self.app_capacity == "auto" and cfg.grad_enabled:
+            cfg.app_cap = self._app_tracker.capacity(center.reshape(-1, 3).shape[0], center.reshape(-1, 3).shape[0] * n_samples)
+            cfg.app_monitor = self._app_tracker.submit
+        elif isinstance(self.app_capacity, (int, float)) and not isinstance(self.app_capacity, bool):
+            cap_all = center.reshape(-1, 3).shape[0] * n_samples
+            cfg.app_cap = int(self.app_capacity * cap_all) if self.app_capacity <= 1.0 else int(self.app_capacity)
         cfg.bf16_backward_taps = bool(getattr(self, "bf16_backward_taps", False))
         # the bf16 copies are cached per (storage, version) only for the module's own Parameters: blurred factors
         # are fresh buffers every call (an address + version key could alias a previous step's buffer)
@@ -599,6 +664,7 @@ class B200_VMSplit(torch.nn.Module):
         self.update_stepSize(res_target)
         self._reg_cache = None
         self._store_cache = ({}, {})
+        self._app_tracker.reset()
 
     def _dense_tables(self, gridSize):
         return [torch.linspace(0, 1, int(g)).to(self.device) for g in gridSize]
@@ -663,8 +729,16 @@ class B200_VMSplit(torch.nn.Module):
         self.aabb = new_aabb
         self._reg_cache = None
         self._store_cache = ({}, {})
+        self._app_tracker.reset()
         new_size = b_r - t_l
         self.update_stepSize((int(new_size[0]), int(new_size[1]), int(new_size[2])))
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._store_cache = ({}, {})           # new factor values: bf16 copies and the appearance-count history are stale
+        self._app_tracker.reset()
+        self._reg_cache = None
+        return out
 
     # ---------------------------------------------------------------- checkpoint side-state (tensorBase.py:508-552)
     def get_reset_kwargs(self):

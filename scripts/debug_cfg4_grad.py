@@ -86,3 +86,32 @@ print("per-sample dL/dsigma_feat: mine vs ref32", rel(mine_s, gs32), " mine vs f
 dif = (mine_s.double() - gs64).abs()
 j = int(dif.argmax())
 print("worst sample", j, "mine", float(mine_s[j]), "ref32", float(gs32[j]), "f64", float(gs64[j]), "max|g|", float(gs64.abs().max()))
+
+# ---- structure of the per-sample differences: which rays / which depth along the ray?
+sid = comp.sidx[:V].cpu().long()
+ray, kk = sid // S, sid % S
+d_m, d_r = (mine_s.double() - gs64), (gs32.double() - gs64)
+scale = float(gs64.abs().max())
+for name, dd_ in (("mine-f64", d_m), ("ref32-f64", d_r), ("mine-ref32", mine_s.double() - gs32.double())):
+    per_ray_abs = torch.zeros(n, dtype=torch.float64).index_add_(0, ray, dd_.abs())
+    per_ray_sgn = torch.zeros(n, dtype=torch.float64).index_add_(0, ray, dd_)
+    coh = float((per_ray_sgn.abs() / per_ray_abs.clamp_min(1e-300)).mean())
+    print(f"{name}: max {float(dd_.abs().max())/scale:.2e} rms {float(dd_.pow(2).mean().sqrt())/scale:.2e} "
+          f"mean sign-coherence per ray {coh:.3f}; worst ray {int(per_ray_abs.argmax())}")
+top = torch.topk(d_m.abs(), 8).indices
+for t_ in top.tolist():
+    print(f"  sample {t_}: ray {int(ray[t_])} k {int(kk[t_])} mine {float(mine_s[t_]):.6e} ref32 {float(gs32[t_]):.6e} f64 {float(gs64[t_]):.6e}")
+# the same for the values feeding the backward: weights and transmittance
+w32 = det32["weight"][det32["valid"]]; w64 = det64["weight"][det64["valid"]]
+print("oracle weights ref32 vs f64 (rel to max):", rel(w32, w64))
+
+mw = cap["weight"][:V].cpu()
+print("my weights vs ref32:", rel(mw, w32), " vs f64:", rel(mw, w64))
+msf = cap["sigfeat"][:V].cpu()
+print("my sigma_feat vs ref32:", rel(msf, det32["sigma_feat"].detach()), " vs f64:", rel(msf, det64["sigma_feat"].detach()),
+      " ref32 vs f64:", rel(det32["sigma_feat"].detach(), det64["sigma_feat"].detach()))
+A_ = int(cap["a_count"].item())
+mrgb = cap["rgb"][:A_, :3].cpu()
+r32 = det32["rgb"][det32["app_mask"]]; r64 = det64["rgb"][det64["app_mask"]]
+print("my rgb vs ref32:", float((mrgb - r32).abs().max()), " vs f64:", float((mrgb.double() - r64).abs().max()),
+      " ref32 vs f64:", float((r32.double() - r64).abs().max()))

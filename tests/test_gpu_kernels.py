@@ -164,3 +164,55 @@ def test_vector_red_accumulates_collisions():
     m.density_plane[0].grad = None
     one.sum().backward()
     assert rel_err(g_all, 4096 * m.density_plane[0].grad) <= 1e-4
+
+
+def test_appearance_capacity_bound_and_tracker():
+    """Memory model of the appearance stage: a bounded capacity truncates the appearance list safely and
+    raises the device flag; the automatic tracker engages after a few training calls, sizes the stage from the
+    observed counts, and a later overflow makes the next forward raise."""
+    import joint_tensorf_b200 as jt
+    from common import load_golden
+    from gpu_common import default_opt, forward_kwargs, module_from_golden
+    g = load_golden("cubic_mlp")
+    m = module_from_golden(g, DEV)
+    opt = default_opt("MLP_Fea")
+    o, d = g["rays_o"].to(DEV), g["rays_d"].to(DEV)
+    fkw = forward_kwargs(g, DEV)
+    m.app_capacity = None
+    og = o.clone().requires_grad_(True)
+    ref = m.forward(opt, og, d, **fkw)
+    a_full = int(jt.VMRender.last_counts[1].item())
+    assert a_full > 1000 and int(jt.VMRender.last_app_used[1].item()) == 0
+    # explicit bound below A: flagged, finite, backward runs, nothing is overrun
+    m.app_capacity = a_full // 2
+    og2 = o.clone().requires_grad_(True)
+    out = m.forward(opt, og2, d, **fkw)
+    used = jt.VMRender.last_app_used.tolist()
+    assert used == [a_full // 2, 1] and int(jt.VMRender.last_counts[1].item()) == a_full
+    out[0].sum().backward()
+    assert torch.isfinite(og2.grad).all() and all(torch.isfinite(t).all() for t in out)
+    assert not torch.equal(out[0], ref[0])
+    # automatic tracking: exact results while it learns, then a bounded stage with identical results
+    m.app_capacity = "auto"
+    m._app_tracker.reset()
+    for _ in range(m._app_tracker.warm + 3):
+        og3 = o.clone().requires_grad_(True)
+        out = m.forward(opt, og3, d, **fkw)
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], ref[0])
+    cap_now = m._app_tracker.capacity(o.shape[0], o.shape[0] * g["n_samples"])
+    assert cap_now is not None and a_full <= cap_now <= o.shape[0] * g["n_samples"]
+    # a sudden 50x denser request than the history allows: flagged, and the NEXT forward raises
+    m._app_tracker.max_per_ray, m._app_tracker.floor = 1e-3, 16
+    out = m.forward(opt, o.clone().requires_grad_(True), d, **fkw)
+    torch.cuda.synchronize()
+    assert int(jt.VMRender.last_app_used[1].item()) == 1
+    with pytest.raises(jt._lib.JtError):
+        m.forward(opt, o.clone().requires_grad_(True), d, **fkw)
+    # ... after which the capacity is unbounded again
+    out = m.forward(opt, o.clone().requires_grad_(True), d, **fkw)
+    assert torch.equal(out[0], ref[0])
+    # no-grad calls allocate exactly (host read of A) and reproduce the training colours
+    with torch.no_grad():
+        out_ng = m.forward(opt, o, d, **fkw)
+    assert (out_ng[0] - ref[0]).abs().max() <= 1e-6

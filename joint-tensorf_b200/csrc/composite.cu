@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp; r < n_rays; r += nwarps) {
         const int b = off[r], e = off[r + 1];
-        float carry = 1.0f, acc = 0.f, wz = 0.f;
+        double carry = 1.0;
+        float acc = 0.f, wz = 0.f;
         int cnt = 0;
         // the inputs of the next 32 samples are requested before the current ones are scanned (one warp per ray:
         // every exposed memory latency is paid ~18 times in a row)
@@ -49,15 +50,20 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
                 q = 1.0f - alpha + 1e-10f;
                 z = cz;
             }
-            float p = q;                                     // inclusive product scan over the warp
+            // Inclusive product scan over the warp, in DOUBLE: the reference's torch.cumprod accumulates in double on
+            // the CPU (ATen cumprod_cpu_kernel: at::acc_type<float, false>) and rounds every prefix to fp32 once, so
+            // T_j carries one rounding instead of j; a float scan here was the largest single difference to the
+            // reference's weights / gradients at the front of long opaque rays. One DMUL per level: free next to
+            // the memory latency this one-warp-per-ray kernel waits on.
+            double p = (double)q;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                float v = __shfl_up_sync(0xffffffffu, p, o);
+                double v = __shfl_up_sync(0xffffffffu, p, o);
                 if (lane >= o) p *= v;
             }
-            float excl = __shfl_up_sync(0xffffffffu, p, 1);
-            if (lane == 0) excl = 1.0f;
-            const float T = carry * excl;
+            double excl = __shfl_up_sync(0xffffffffu, p, 1);
+            if (lane == 0) excl = 1.0;
+            const float T = (float)(carry * excl);
             const float w = alpha * T;
             if (j < e) {
                 weight[j] = w;
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
             gm[c] = (pre >= 0.0f && pre <= 1.0f) ? g_rgb[3 * r + c] : 0.0f;      // clamp backward
         }
         const float dacc = (g_acc ? g_acc[r] : 0.0f) - (white_bg ? (gm[0] + gm[1] + gm[2]) : 0.0f);
-        float carry = 0.f, dn = 0.f;
+        double carry = 0.0;
+        float dn = 0.f;
         const int len = e - b;
         for (int i0 = 0; i0 < len; i0 += 32) {
             const int i = i0 + lane;                 // reverse index: j = e-1-i
@@ -209,28 +216,29 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
                 }
             }
             // per-sample factors of the recurrence (identity map for lanes past the ray's first sample)
-            float x = 0.f, sigma = 0.f, dd = 0.f, ex = 1.f, A = 0.f, Q = 1.f;
+            float x = 0.f, sigma = 0.f, dd = 0.f, ex = 1.f;
+            double A = 0.0, Q = 1.0;                 // double like the forward scan (and the reference's CPU cumsum)
             if (i < len) {
                 x = sf + shift;
                 sigma = density_act(x, act);
                 dd = dj * dscale;
                 ex = exp_neg(-sigma * dd);
                 const float alpha = 1.0f - ex;
-                Q = 1.0f - alpha + 1e-10f;
-                A = dw * alpha;
+                Q = (double)(1.0f - alpha + 1e-10f);
+                A = (double)dw * (double)alpha;
             }
             // inclusive scan, in reverse sample order, of the affine maps y -> A + Q y (composition:
             // (A, Q) o (A', Q') = (A + Q A', Q Q')); lane i then maps the value behind the chunk to Y in front of sample j_i
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const float a2 = __shfl_up_sync(0xffffffffu, A, o), q2 = __shfl_up_sync(0xffffffffu, Q, o);
-                if (lane >= o) { A = fmaf(Q, a2, A); Q *= q2; }
+                const double a2 = __shfl_up_sync(0xffffffffu, A, o), q2 = __shfl_up_sync(0xffffffffu, Q, o);
+                if (lane >= o) { A = fma(Q, a2, A); Q *= q2; }
             }
-            const float zin = fmaf(Q, carry, A);     // Y in front of this lane's sample (includes it)
-            float ybehind = __shfl_up_sync(0xffffffffu, zin, 1);
+            const double zin = fma(Q, carry, A);     // Y in front of this lane's sample (includes it)
+            double ybehind = __shfl_up_sync(0xffffffffu, zin, 1);
             if (lane == 0) ybehind = carry;          // Y_j: everything behind sample j
             if (i < len) {
-                const float dalpha = tj * (dw - ybehind);
+                const float dalpha = (float)((double)tj * ((double)dw - ybehind));
                 const float dsigma = dalpha * dd * ex;
                 dsig[j] = dsigma * density_act_grad(x, act);
                 dn += dalpha * sigma * ex * dd;      // d/d(norm) * norm

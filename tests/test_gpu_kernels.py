@@ -215,4 +215,4 @@ def test_appearance_capacity_bound_and_tracker():
     # no-grad calls allocate exactly (host read of A) and reproduce the training colours
     with torch.no_grad():
         out_ng = m.forward(opt, o, d, **fkw)
-    assert (out_ng[0] - ref[0]).abs().max() <= 1e-6
+    assert (out_ng[0] - ref[0]).abs().max() <= 1e-4      # the no-grad MLP_Fea head takes fp16 operand tiles

@@ -538,7 +538,7 @@ def own_arm(args):
 
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # > 126 MB L2
 
-    def timed(fn, k):
+    def timed(fn, k, align=False):
         """Sum of the K per-step device times (CUDA events on the launching stream). The L2
         flush between steps is on the stream but outside every event pair; the host does not
         synchronise inside the loop, so it queues launches ahead as a training loop does."""
@@ -550,7 +550,7 @@ def own_arm(args):
         # every later step; nothing inside an event pair changes.
         for _ in range(6):
             flush.fill_(1.0)
-        if world > 1:
+        if world > 1 and align:      # (collective: only where every rank calls timed(), never in rank-0-only sections)
             # device-side rendezvous in front of the first timed step: the hosts reach this point a few ms apart
             # (thread start-up, GC), and without it rank 0's first gradient all-reduce waits for the last rank to
             # arrive -- 6.85 ms instead of 3.2 ms for the first of the 20 steps in SCALE_r01 at N = 8. The hosts keep
@@ -590,11 +590,11 @@ def own_arm(args):
     barrier()
     l0 = jt._lib.launch_count()
     with ClockSampler(local) as clk:             # clocks are sampled across both timed regions
-        ms = timed(lambda: step(pix_d, tgt_d), args.steps)
+        ms = timed(lambda: step(pix_d, tgt_d), args.steps, align=True)
         host_ms, per_step = timed.host_ms, timed.per_step
         barrier()
         launches = jt._lib.launch_count() - l0
-        ms_e2e = timed(step_e2e, args.steps)
+        ms_e2e = timed(step_e2e, args.steps, align=True)
         barrier()
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -749,6 +749,21 @@ def own_arm(args):
         del model_o, step_o
         torch.cuda.empty_cache()
 
+    # the strict-fp32 row: the headline workload with head_precision="fp32" (SIMT fp32 GEMMs, gradients within 1e-4 of
+    # the reference instead of the 2e-2 class of the bf16-operand backward GEMMs), same protocol
+    strict = None
+    if rank == 0 and world == 1 and args.head != "fp32" and not args.no_also and args.blur == 0:
+        model.head_precision = "fp32"
+        for _ in range(3):
+            step(pix_d, tgt_d, reduce=False)
+        torch.cuda.synchronize()
+        ms_s = timed(lambda: step(pix_d, tgt_d, reduce=False), args.steps)
+        strict = {"workload": jt.synth.describe(args.workload, N) + ", head_precision=fp32 (strict parity path)",
+                  "value": N * args.steps / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
+                  "steps": args.steps, "dtype": "f32"}
+        model.head_precision = args.head
+        torch.cuda.empty_cache()
+
     # next rows of SURVEY 8f, timed after everything above because the optimiser changes the parameters:
     # 8f-2 a full training iteration = the step above + density_L1 regulariser (Blender weight 8e-5, TV weights 0,
     # bat_blender_VM.yaml:134-139) + Adam update of every parameter; 8f-3 the between-step maintenance ops.
@@ -865,6 +880,8 @@ def own_arm(args):
             line["render_800x800"] = render
         if also is not None:
             line["also"] = also
+        if strict is not None:
+            line["strict_fp32"] = strict
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if aten is not None:

@@ -20,6 +20,10 @@ namespace jt {
 // ------------------------------------------------------------------ forward, pass A
 // per ray: sigma -> alpha -> T (exclusive product scan) -> weight; accumulates acc
 // and sum(w*z); counts appearance samples (w > thres).
+// Each lane owns KS consecutive samples of a 32*KS-sample block: one warp scan per block instead of one per 32
+// samples, and KS independent loads in flight per lane (the kernel is one warp per ray and latency-bound: with KS = 1
+// it reached 30 % of the HBM rate of its 40 bytes per sample).
+constexpr int KS = 4;
 __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ off, int n_rays,
                                                         const float* __restrict__ sigfeat,
                                                         const float* __restrict__ dist,
@@ -35,27 +39,38 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
         double carry = 1.0;
         float acc = 0.f, wz = 0.f;
         int cnt = 0;
-        // the inputs of the next 32 samples are requested before the current ones are scanned (one warp per ray:
-        // every exposed memory latency is paid ~18 times in a row)
-        float nsf = 0.f, ndj = 0.f, nz = 0.f;
-        if (b + lane < e) { nsf = sigfeat[b + lane]; ndj = dist[b + lane]; nz = samp[b + lane].w; }
-        for (int j0 = b; j0 < e; j0 += 32) {
-            const int j = j0 + lane;
-            const float csf = nsf, cdj = ndj, cz = nz;
-            if (j + 32 < e) { nsf = sigfeat[j + 32]; ndj = dist[j + 32]; nz = samp[j + 32].w; }
-            float q = 1.0f, alpha = 0.f, z = 0.f;
-            if (j < e) {
-                float sigma = density_act(csf + shift, act);
-                alpha = 1.0f - exp_neg(-sigma * (cdj * dscale));
-                q = 1.0f - alpha + 1e-10f;
-                z = cz;
+        // the inputs of the next block are requested before the current one is scanned
+        float nsf[KS], ndj[KS], nz[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const int j = b + lane * KS + k;
+            nsf[k] = ndj[k] = nz[k] = 0.f;
+            if (j < e) { nsf[k] = sigfeat[j]; ndj[k] = dist[j]; nz[k] = samp[j].w; }
+        }
+        for (int j0 = b; j0 < e; j0 += 32 * KS) {
+            const int jl = j0 + lane * KS;                   // first sample of this lane
+            float q[KS], alpha[KS], z[KS];
+            double pl = 1.0;                                 // product of this lane's q (double, see below)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                q[k] = 1.0f; alpha[k] = 0.f; z[k] = nz[k];
+                if (jl + k < e) {
+                    const float sigma = density_act(nsf[k] + shift, act);
+                    alpha[k] = 1.0f - exp_neg(-sigma * (ndj[k] * dscale));
+                    q[k] = 1.0f - alpha[k] + 1e-10f;
+                }
+                pl *= (double)q[k];
+            }
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const int j = jl + 32 * KS + k;
+                if (j < e) { nsf[k] = sigfeat[j]; ndj[k] = dist[j]; nz[k] = samp[j].w; }
             }
             // Inclusive product scan over the warp, in DOUBLE: the reference's torch.cumprod accumulates in double on
             // the CPU (ATen cumprod_cpu_kernel: at::acc_type<float, false>) and rounds every prefix to fp32 once, so
             // T_j carries one rounding instead of j; a float scan here was the largest single difference to the
-            // reference's weights / gradients at the front of long opaque rays. One DMUL per level: free next to
-            // the memory latency this one-warp-per-ray kernel waits on.
-            double p = (double)q;
+            // reference's weights / gradients at the front of long opaque rays.
+            double p = pl;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 double v = __shfl_up_sync(0xffffffffu, p, o);
@@ -63,15 +78,24 @@ __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ 
             }
             double excl = __shfl_up_sync(0xffffffffu, p, 1);
             if (lane == 0) excl = 1.0;
-            const float T = (float)(carry * excl);
-            const float w = alpha * T;
-            if (j < e) {
-                weight[j] = w;
-                trans[j] = T;
-                acc += w;
-                wz += w * z;
+            double Td = carry * excl;                        // transmittance in front of this lane's first sample
+            bool pass[KS];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const float T = (float)Td;
+                const float w = alpha[k] * T;
+                pass[k] = false;
+                if (jl + k < e) {
+                    weight[jl + k] = w;
+                    trans[jl + k] = T;
+                    acc += w;
+                    wz += w * z[k];
+                    pass[k] = w > thres;
+                }
+                Td *= (double)q[k];
             }
-            cnt += __popc(__ballot_sync(0xffffffffu, (j < e) && (w > thres)));
+#pragma unroll
+            for (int k = 0; k < KS; ++k) cnt += __popc(__ballot_sync(0xffffffffu, pass[k]));
             carry *= __shfl_sync(0xffffffffu, p, 31);
         }
         acc = warp_sum(acc);
@@ -196,52 +220,61 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
         double carry = 0.0;
         float dn = 0.f;
         const int len = e - b;
-        for (int i0 = 0; i0 < len; i0 += 32) {
-            const int i = i0 + lane;                 // reverse index: j = e-1-i
-            const int j = e - 1 - i;
-            float dw = 0.f, w = 0.f;
-            float sf = 0.f, dj = 0.f, tj = 0.f;      // inputs of the second half, requested before the scan: the
-            if (i < len) {                           // kernel is one warp per ray and pays every exposed latency
-                w = weight[j];
-                sf = sigfeat[j]; dj = dist[j]; tj = trans[j];
-                dw = dacc;
-                const int a = app_of[j];
-                if (a >= 0) {
-                    const float r0 = rgb[4 * (size_t)a + 0], r1 = rgb[4 * (size_t)a + 1], r2 = rgb[4 * (size_t)a + 2];
-                    dw += gm[0] * r0 + gm[1] * r1 + gm[2] * r2;
-                    float d0 = w * gm[0], d1 = w * gm[1], d2 = w * gm[2];
-                    if (shade_act == 1) { d0 *= r0 * (1.f - r0); d1 *= r1 * (1.f - r1); d2 *= r2 * (1.f - r2); }
-                    else if (shade_act == 2) { d0 = r0 > 0.f ? d0 : 0.f; d1 = r1 > 0.f ? d1 : 0.f; d2 = r2 > 0.f ? d2 : 0.f; }
-                    *reinterpret_cast<float4*>(dout + 4 * (size_t)a) = make_float4(d0, d1, d2, 0.f);
+        // lane owns KS consecutive samples in REVERSE order: i = i0 + lane*KS + k, j = e-1-i
+        for (int i0 = 0; i0 < len; i0 += 32 * KS) {
+            float dw[KS], tj[KS], xx[KS], sg[KS], dd[KS], ex[KS], al[KS], qf[KS];
+            int jj[KS];
+            double A = 0.0, Q = 1.0;                 // composite of this lane's affine maps, double like the forward scan
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const int i = i0 + lane * KS + k;
+                const int j = e - 1 - i;
+                jj[k] = i < len ? j : -1;
+                dw[k] = 0.f; tj[k] = 0.f; xx[k] = 0.f; sg[k] = 0.f; dd[k] = 0.f; ex[k] = 1.f; al[k] = 0.f; qf[k] = 1.f;
+                if (i < len) {
+                    const float w = weight[j];
+                    const float sf = sigfeat[j], dj = dist[j];
+                    tj[k] = trans[j];
+                    dw[k] = dacc;
+                    const int a = app_of[j];
+                    if (a >= 0) {
+                        const float4 c4 = *reinterpret_cast<const float4*>(rgb + 4 * (size_t)a);
+                        const float r0 = c4.x, r1 = c4.y, r2 = c4.z;
+                        dw[k] += gm[0] * r0 + gm[1] * r1 + gm[2] * r2;
+                        float d0 = w * gm[0], d1 = w * gm[1], d2 = w * gm[2];
+                        if (shade_act == 1) { d0 *= r0 * (1.f - r0); d1 *= r1 * (1.f - r1); d2 *= r2 * (1.f - r2); }
+                        else if (shade_act == 2) { d0 = r0 > 0.f ? d0 : 0.f; d1 = r1 > 0.f ? d1 : 0.f; d2 = r2 > 0.f ? d2 : 0.f; }
+                        *reinterpret_cast<float4*>(dout + 4 * (size_t)a) = make_float4(d0, d1, d2, 0.f);
+                    }
+                    xx[k] = sf + shift;
+                    sg[k] = density_act(xx[k], act);
+                    dd[k] = dj * dscale;
+                    ex[k] = exp_neg(-sg[k] * dd[k]);
+                    al[k] = 1.0f - ex[k];
+                    qf[k] = 1.0f - al[k] + 1e-10f;
                 }
+                // z_i = a_i + q_i z_{i-1}: apply this sample's map on top of the lane's composite so far
+                A = fma((double)qf[k], A, (double)dw[k] * (double)al[k]);
+                Q *= (double)qf[k];
             }
-            // per-sample factors of the recurrence (identity map for lanes past the ray's first sample)
-            float x = 0.f, sigma = 0.f, dd = 0.f, ex = 1.f;
-            double A = 0.0, Q = 1.0;                 // double like the forward scan (and the reference's CPU cumsum)
-            if (i < len) {
-                x = sf + shift;
-                sigma = density_act(x, act);
-                dd = dj * dscale;
-                ex = exp_neg(-sigma * dd);
-                const float alpha = 1.0f - ex;
-                Q = (double)(1.0f - alpha + 1e-10f);
-                A = (double)dw * (double)alpha;
-            }
-            // inclusive scan, in reverse sample order, of the affine maps y -> A + Q y (composition:
-            // (A, Q) o (A', Q') = (A + Q A', Q Q')); lane i then maps the value behind the chunk to Y in front of sample j_i
+            // inclusive scan over the lanes of the composites (A, Q) o (A', Q') = (A + Q A', Q Q')
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const double a2 = __shfl_up_sync(0xffffffffu, A, o), q2 = __shfl_up_sync(0xffffffffu, Q, o);
                 if (lane >= o) { A = fma(Q, a2, A); Q *= q2; }
             }
-            const double zin = fma(Q, carry, A);     // Y in front of this lane's sample (includes it)
-            double ybehind = __shfl_up_sync(0xffffffffu, zin, 1);
-            if (lane == 0) ybehind = carry;          // Y_j: everything behind sample j
-            if (i < len) {
-                const float dalpha = (float)((double)tj * ((double)dw - ybehind));
-                const float dsigma = dalpha * dd * ex;
-                dsig[j] = dsigma * density_act_grad(x, act);
-                dn += dalpha * sigma * ex * dd;      // d/d(norm) * norm
+            const double zin = fma(Q, carry, A);     // Y in front of this lane's last (front-most) sample
+            double y = __shfl_up_sync(0xffffffffu, zin, 1);
+            if (lane == 0) y = carry;                // Y behind this lane's first sample
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                if (jj[k] >= 0) {
+                    const float dalpha = (float)((double)tj[k] * ((double)dw[k] - y));
+                    const float dsigma = dalpha * dd[k] * ex[k];
+                    dsig[jj[k]] = dsigma * density_act_grad(xx[k], act);
+                    dn += dalpha * sg[k] * ex[k] * dd[k];      // d/d(norm) * norm
+                }
+                y = fma((double)qf[k], y, (double)dw[k] * (double)al[k]);
             }
             carry = __shfl_sync(0xffffffffu, zin, 31);
         }

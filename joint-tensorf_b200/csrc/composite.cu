@@ -23,7 +23,8 @@ namespace jt {
 // Each lane owns KS consecutive samples of a 32*KS-sample block: one warp scan per block instead of one per 32
 // samples, and KS independent loads in flight per lane (the kernel is one warp per ray and latency-bound: with KS = 1
 // it reached 30 % of the HBM rate of its 40 bytes per sample).
-constexpr int KS = 4;
+constexpr int KS = 4;       // forward (measured: 0.050 -> 0.046 ms for the three launches of jt_alpha_fwd)
+constexpr int KSB = 1;      // backward: 4 samples per lane cost registers (79) and time (0.056 -> 0.062 ms)
 __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ off, int n_rays,
                                                         const float* __restrict__ sigfeat,
                                                         const float* __restrict__ dist,
@@ -220,14 +221,14 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
         double carry = 0.0;
         float dn = 0.f;
         const int len = e - b;
-        // lane owns KS consecutive samples in REVERSE order: i = i0 + lane*KS + k, j = e-1-i
-        for (int i0 = 0; i0 < len; i0 += 32 * KS) {
-            float dw[KS], tj[KS], xx[KS], sg[KS], dd[KS], ex[KS], al[KS], qf[KS];
-            int jj[KS];
+        // lane owns KSB consecutive samples in REVERSE order: i = i0 + lane*KSB + k, j = e-1-i
+        for (int i0 = 0; i0 < len; i0 += 32 * KSB) {
+            float dw[KSB], tj[KSB], xx[KSB], sg[KSB], dd[KSB], ex[KSB], al[KSB], qf[KSB];
+            int jj[KSB];
             double A = 0.0, Q = 1.0;                 // composite of this lane's affine maps, double like the forward scan
 #pragma unroll
-            for (int k = 0; k < KS; ++k) {
-                const int i = i0 + lane * KS + k;
+            for (int k = 0; k < KSB; ++k) {
+                const int i = i0 + lane * KSB + k;
                 const int j = e - 1 - i;
                 jj[k] = i < len ? j : -1;
                 dw[k] = 0.f; tj[k] = 0.f; xx[k] = 0.f; sg[k] = 0.f; dd[k] = 0.f; ex[k] = 1.f; al[k] = 0.f; qf[k] = 1.f;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
             double y = __shfl_up_sync(0xffffffffu, zin, 1);
             if (lane == 0) y = carry;                // Y behind this lane's first sample
 #pragma unroll
-            for (int k = 0; k < KS; ++k) {
+            for (int k = 0; k < KSB; ++k) {
                 if (jj[k] >= 0) {
                     const float dalpha = (float)((double)tj[k] * ((double)dw[k] - y));
                     const float dsigma = dalpha * dd[k] * ex[k];

@@ -63,7 +63,7 @@ struct FwdSmem {
 // PE of one scalar with 2 frequencies (tensorBase.py:43-55): [sin x, sin 2x, cos x, cos 2x] with annealing masks
 __device__ __forceinline__ void pe4(float x, float m0, float m1, float v[4]) {
     float s, c;
-    sincosf(x, &s, &c);
+    fast_sincos(x, &s, &c);              // Cody-Waite reduction + SFU (abs error ~2^-21), as the MLP_Fea head does
     v[0] = s * m0; v[1] = (2.f * s * c) * m1; v[2] = c * m0; v[3] = (1.f - 2.f * s * s) * m1;
 }
 
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(NT) wv_head_bwd_data_kernel(const float* __res
             }
             auto chain = [&](int e, const float* g) {               // g = d/d[sin x, sin 2x, cos x, cos 2x]
                 float sn, co;
-                sincosf(feat[e], &sn, &co);
+                fast_sincos(feat[e], &sn, &co);
                 const float s2 = 2.f * sn * co, c2 = 1.f - 2.f * sn * sn;
                 df[e] += pf0 * (co * g[0] - sn * g[2]) + 2.f * pf1 * (c2 * g[1] - s2 * g[3]);
             };

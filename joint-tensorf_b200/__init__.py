@@ -7,7 +7,7 @@ Public surface (mirrors reference `model.tensorf_repr`):
 Lower level: `ops` (C-ABI wrappers), `render.VMRender` (fused autograd node),
 `synth` (deterministic synthetic scenes/rays), `parallel` (ray-sharded data parallel).
 """
-from . import _lib, camera, ops, options, synth  # noqa: F401
+from . import _lib, camera, graphs, ops, options, synth  # noqa: F401
 from .render import RenderCfg, VMRender  # noqa: F401
 from .vmsplit import AlphaGridMask, B200_VMSplit  # noqa: F401
 

@@ -216,3 +216,45 @@ def test_appearance_capacity_bound_and_tracker():
     with torch.no_grad():
         out_ng = m.forward(opt, o, d, **fkw)
     assert (out_ng[0] - ref[0]).abs().max() <= 1e-4      # the no-grad MLP_Fea head takes fp16 operand tiles
+
+
+def test_cuda_graph_replay_of_a_training_step():
+    """joint_tensorf_b200.graphs.GraphedStep: forward + loss + backward captured once and replayed reproduces the
+    eagerly executed step (deterministic inputs: injected jitter, white background), and follows in-place updates of
+    its static inputs."""
+    import joint_tensorf_b200 as jt
+    from common import load_golden
+    from gpu_common import default_opt, forward_kwargs, module_from_golden
+    g = load_golden("sh_vm48")
+    m = module_from_golden(g, DEV)
+    m.head_precision = "tc"
+    m.app_capacity = None
+    opt = default_opt("SH")
+    fkw = forward_kwargs(g, DEV)
+    o_s = g["rays_o"].to(DEV).clone().requires_grad_(True)
+    d_s = g["rays_d"].to(DEV).clone()
+    w = g["w_rgb"].to(DEV)
+    params = list(m.parameters())
+
+    def fn():
+        for p in params + [o_s]:
+            p.grad = None
+        rgb, depth, acc = m.forward(opt, o_s, d_s, **fkw)
+        loss = (rgb * w).sum()
+        loss.backward()
+        return loss.detach(), rgb.detach()
+
+    loss_e, rgb_e = (t.clone() for t in fn())
+    g_app_e, g_o_e = m.app_plane[1].grad.clone(), o_s.grad.clone()
+    graphed = jt.graphs.GraphedStep(fn, warmup=2)
+    loss_g, rgb_g = graphed()
+    torch.cuda.synchronize()
+    assert torch.equal(rgb_g, rgb_e) and torch.equal(loss_g, loss_e)
+    assert rel_err(m.app_plane[1].grad, g_app_e) <= 1e-5 and rel_err(o_s.grad, g_o_e) <= 1e-5     # atomics reorder sums
+    # new ray directions through the same static buffer
+    with torch.no_grad():
+        d_s.copy_(d_s.flip(0))
+    loss_g2, rgb_g2 = (t.clone() for t in graphed())
+    loss_e2, rgb_e2 = fn()
+    torch.cuda.synchronize()
+    assert torch.equal(rgb_g2, rgb_e2) and not torch.equal(rgb_g2, rgb_e)

@@ -534,6 +534,8 @@ def own_arm(args):
     step = make_step(model, opt, params)
     eager_step = step
     launches_per_graph = None
+    if args.cuda_graph and world > 1:
+        raise SystemExit("--cuda-graph: the data-parallel step (NCCL all-reduces inside autograd) is not captured; N = 1 only")
     if args.cuda_graph:
         # the whole step as ONE graph launch: static input buffers refreshed in place, static loss / gradients
         model.app_capacity = None                    # the automatic capacity tracker polls events: not capturable
@@ -786,6 +788,24 @@ def own_arm(args):
         model.head_precision = args.head
         torch.cuda.empty_cache()
 
+    # the same step replayed from a CUDA graph (joint_tensorf_b200.graphs.GraphedStep): what the ~45 ctypes launches per
+    # step cost on the host, and what a launch-bound batch gains (512 rays = the per-GPU share of a strong-scaled
+    # 4096-ray step on 8 GPUs)
+    graph_row = None
+    if rank == 0 and world == 1 and not args.cuda_graph and not args.no_also and args.blur == 0:
+        try:
+            model.app_capacity = None
+            pix_g, tgt_g = pix_d.clone(), tgt_d.clone()
+            gs = jt.graphs.GraphedStep(lambda: eager_step(pix_g, tgt_g, reduce=False), warmup=3)
+            ms_g = timed(gs, args.steps)
+            graph_row = {"ms_per_step": ms_g / args.steps, "value": N * args.steps / (ms_g * 1e-3), "unit": UNIT,
+                         "host_enqueue_ms_per_step": round(timed.host_ms, 3),
+                         "what": "the headline step captured once and replayed (one graph launch per step)"}
+            del gs
+        except Exception as ex:          # an optional row must never take the bench line down
+            graph_row = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
+
     # next rows of SURVEY 8f, timed after everything above because the optimiser changes the parameters:
     # 8f-2 a full training iteration = the step above + density_L1 regulariser (Blender weight 8e-5, TV weights 0,
     # bat_blender_VM.yaml:134-139) + Adam update of every parameter; 8f-3 the between-step maintenance ops.
@@ -905,6 +925,8 @@ def own_arm(args):
             line["also"] = also
         if strict is not None:
             line["strict_fp32"] = strict
+        if graph_row is not None:
+            line["cuda_graph_replay"] = graph_row
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if aten is not None:

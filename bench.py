@@ -374,6 +374,10 @@ def compulsory_bytes(name, V, A, fbytes_d, fbytes_a, gbytes_d, gbytes_a, ctot_a,
         # data kernel: dout + feat row + the relu-mask halves of A2 / A3 in, D2 / D1 / DF / DO tiles + dcomps out;
         # weight-gradient kernel: all eight staged tiles (1264 B per sample, head_tc.cuh) in
         "head_bwd_tc": A * (16 + 128 + 256 + 336 + gin_bytes * ctot_a + 1264),
+        # LLFF head: components in (4 B x sum C), feat/dir row + rgb out, 752 B of staged tiles when training;
+        # backward: dout + feat row + mask halves in, D tiles + fp32 dcomps out, weight-gradient kernel reads all tiles
+        "wv_head_fwd_tc": A * (4 * ctot_a + 128 + 16 + (544 if train else 0)),
+        "wv_head_bwd_tc": A * (16 + 128 + 128 + 208 + 4 * ctot_a + 752),
         "alpha_fwd": V * (4 + 4 + 16 + 8 + 8), "render_bwd": V * (4 + 4 + 8 + 4 + 16 + 16 + 4),
         "composite_fwd": A * (4 + 4 + 16),
     }
@@ -399,7 +403,8 @@ SPAN_KERNELS = {
     "vm_density_fwd": ["vm_fwd_kernel<0"], "vm_app_fwd": ["vm_fwd_kernel<1"],
     "app_basis_sh_fwd_tc": ["app_basis_fwd_kernel"], "app_basis_fwd_tc": ["app_basis_fwd_kernel"],
     "sh_bwd_tc": ["sh_bwd_data_kernel", "head_bwd_wgrad_kernel"], "head_mlp_fwd_tc": ["head_mlp_fwd_kernel"],
-    "head_bwd_tc": ["head_bwd_data_kernel", "head_bwd_wgrad_kernel"], "alpha_fwd": ["alpha_fwd_kernel"],
+    "head_bwd_tc": ["head_bwd_data_kernel", "head_bwd_wgrad_kernel"], "alpha_fwd": ["alpha_fwd_kernel", "app_fill_kernel"],
+    "wv_head_fwd_tc": ["wv::wv_head_fwd_kernel"], "wv_head_bwd_tc": ["wv::wv_head_bwd_data_kernel", "wv::wv_head_bwd_wgrad_kernel"],
     "render_bwd": ["render_bwd_kernel"], "composite_fwd": ["composite_fwd_kernel"],
 }
 

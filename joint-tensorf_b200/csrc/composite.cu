@@ -24,7 +24,7 @@ namespace jt {
 // samples, and KS independent loads in flight per lane (the kernel is one warp per ray and latency-bound: with KS = 1
 // it reached 30 % of the HBM rate of its 40 bytes per sample).
 constexpr int KS = 4;       // forward (measured: 0.050 -> 0.046 ms for the three launches of jt_alpha_fwd)
-constexpr int KSB = 1;      // backward: 4 samples per lane cost registers (79) and time (0.056 -> 0.062 ms)
+// (the backward keeps one sample per lane: four cost registers (79) and time, 0.056 -> 0.062 ms; it is software-pipelined instead)
 __global__ void __launch_bounds__(256) alpha_fwd_kernel(const int* __restrict__ off, int n_rays,
                                                         const float* __restrict__ sigfeat,
                                                         const float* __restrict__ dist,
@@ -125,17 +125,27 @@ __global__ void __launch_bounds__(256) app_fill_kernel(const int* __restrict__ o
     for (int r = warp; r < n_rays; r += nwarps) {
         const int b = off[r], e = off[r + 1];
         int base = aoff[r];
-        for (int j0 = b; j0 < e; j0 += 32) {
-            const int j = j0 + lane;
-            const bool ok = (j < e) && (weight[j] > thres);
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (j < e) {
-                int a = ok ? base + __popc(m & ((1u << lane) - 1u)) : -1;
-                if (a >= app_cap) a = -1;
-                app_of[j] = a;
-                if (a >= 0) aidx[a] = j;
+        // four 32-sample chunks per iteration: their loads are independent (one warp per ray: latency-bound)
+        for (int j0 = b; j0 < e; j0 += 128) {
+            float wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                wv[u] = j < e ? weight[j] : 0.f;
             }
-            base += __popc(m);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 32 * u + lane;
+                const bool ok = (j < e) && (wv[u] > thres);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (j < e) {
+                    int a = ok ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+                    if (a >= app_cap) a = -1;
+                    app_of[j] = a;
+                    if (a >= 0) aidx[a] = j;
+                }
+                base += __popc(m);
+            }
         }
     }
 }
@@ -158,11 +168,20 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const int* __restric
     for (int r = warp; r < n_rays; r += nwarps) {
         const int b = min(aoff[r], app_cap), e = min(aoff[r + 1], app_cap);
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        for (int a = b + lane; a < e; a += 32) {
-            const float w = weight[aidx[a]];
-            c0 += w * rgb[4 * (size_t)a + 0];
-            c1 += w * rgb[4 * (size_t)a + 1];
-            c2 += w * rgb[4 * (size_t)a + 2];
+        for (int a0 = b + lane; a0 < e; a0 += 128) {        // four entries per lane in flight: index -> weight is a
+            int jx[4];                                        // dependent gather, the colours are independent loads
+            float4 cv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int a = a0 + 32 * u;
+                jx[u] = a < e ? aidx[a] : -1;
+                cv[u] = a < e ? __ldcs(reinterpret_cast<const float4*>(rgb) + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float w = jx[u] >= 0 ? weight[jx[u]] : 0.f;
+                c0 += w * cv[u].x; c1 += w * cv[u].y; c2 += w * cv[u].z;
+            }
         }
         c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
         if (lane == 0) {
@@ -221,63 +240,68 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const int* __restrict__
         double carry = 0.0;
         float dn = 0.f;
         const int len = e - b;
-        // lane owns KSB consecutive samples in REVERSE order: i = i0 + lane*KSB + k, j = e-1-i
-        for (int i0 = 0; i0 < len; i0 += 32 * KSB) {
-            float dw[KSB], tj[KSB], xx[KSB], sg[KSB], dd[KSB], ex[KSB], al[KSB], qf[KSB];
-            int jj[KSB];
-            double A = 0.0, Q = 1.0;                 // composite of this lane's affine maps, double like the forward scan
-#pragma unroll
-            for (int k = 0; k < KSB; ++k) {
-                const int i = i0 + lane * KSB + k;
+        // Reverse index i = i0 + lane, sample j = e-1-i. Software pipeline over the 32-sample chunks (one warp per ray:
+        // every exposed latency is paid ~20 times in a row): while chunk c is scanned, the per-sample inputs of chunk
+        // c+2 and the colours of chunk c+1 (a dependent gather through app_of) are already in flight.
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_vals = [&](int i, float& w, float& sf, float& dj, float& tj, int& a) {
+            w = 0.f; sf = 0.f; dj = 0.f; tj = 0.f; a = -1;
+            if (i < len) {
                 const int j = e - 1 - i;
-                jj[k] = i < len ? j : -1;
-                dw[k] = 0.f; tj[k] = 0.f; xx[k] = 0.f; sg[k] = 0.f; dd[k] = 0.f; ex[k] = 1.f; al[k] = 0.f; qf[k] = 1.f;
-                if (i < len) {
-                    const float w = weight[j];
-                    const float sf = sigfeat[j], dj = dist[j];
-                    tj[k] = trans[j];
-                    dw[k] = dacc;
-                    const int a = app_of[j];
-                    if (a >= 0) {
-                        const float4 c4 = *reinterpret_cast<const float4*>(rgb + 4 * (size_t)a);
-                        const float r0 = c4.x, r1 = c4.y, r2 = c4.z;
-                        dw[k] += gm[0] * r0 + gm[1] * r1 + gm[2] * r2;
-                        float d0 = w * gm[0], d1 = w * gm[1], d2 = w * gm[2];
-                        if (shade_act == 1) { d0 *= r0 * (1.f - r0); d1 *= r1 * (1.f - r1); d2 *= r2 * (1.f - r2); }
-                        else if (shade_act == 2) { d0 = r0 > 0.f ? d0 : 0.f; d1 = r1 > 0.f ? d1 : 0.f; d2 = r2 > 0.f ? d2 : 0.f; }
-                        *reinterpret_cast<float4*>(dout + 4 * (size_t)a) = make_float4(d0, d1, d2, 0.f);
-                    }
-                    xx[k] = sf + shift;
-                    sg[k] = density_act(xx[k], act);
-                    dd[k] = dj * dscale;
-                    ex[k] = exp_neg(-sg[k] * dd[k]);
-                    al[k] = 1.0f - ex[k];
-                    qf[k] = 1.0f - al[k] + 1e-10f;
-                }
-                // z_i = a_i + q_i z_{i-1}: apply this sample's map on top of the lane's composite so far
-                A = fma((double)qf[k], A, (double)dw[k] * (double)al[k]);
-                Q *= (double)qf[k];
+                w = weight[j]; sf = sigfeat[j]; dj = dist[j]; tj = trans[j]; a = app_of[j];
             }
-            // inclusive scan over the lanes of the composites (A, Q) o (A', Q') = (A + Q A', Q Q')
+        };
+        auto load_rgb = [&](int a) -> float4 { return a >= 0 ? *reinterpret_cast<const float4*>(rgb + 4 * (size_t)a) : zero4; };
+        float w0, sf0, dj0, tj0, w1, sf1, dj1, tj1;
+        int a0, a1;
+        load_vals(lane, w0, sf0, dj0, tj0, a0);
+        load_vals(32 + lane, w1, sf1, dj1, tj1, a1);
+        float4 c0 = load_rgb(a0);
+        for (int i0 = 0; i0 < len; i0 += 32) {
+            const int i = i0 + lane;
+            const float4 c1 = load_rgb(a1);
+            float w2, sf2, dj2, tj2;
+            int a2;
+            load_vals(i + 64, w2, sf2, dj2, tj2, a2);
+            const int j = e - 1 - i;
+            float dw = 0.f, xx = 0.f, sg = 0.f, dd = 0.f, ex = 1.f, al = 0.f, qf = 1.f;
+            if (i < len) {
+                dw = dacc;
+                if (a0 >= 0) {
+                    const float r0 = c0.x, r1 = c0.y, r2 = c0.z;
+                    dw += gm[0] * r0 + gm[1] * r1 + gm[2] * r2;
+                    float d0 = w0 * gm[0], d1 = w0 * gm[1], d2 = w0 * gm[2];
+                    if (shade_act == 1) { d0 *= r0 * (1.f - r0); d1 *= r1 * (1.f - r1); d2 *= r2 * (1.f - r2); }
+                    else if (shade_act == 2) { d0 = r0 > 0.f ? d0 : 0.f; d1 = r1 > 0.f ? d1 : 0.f; d2 = r2 > 0.f ? d2 : 0.f; }
+                    *reinterpret_cast<float4*>(dout + 4 * (size_t)a0) = make_float4(d0, d1, d2, 0.f);
+                }
+                xx = sf0 + shift;
+                sg = density_act(xx, act);
+                dd = dj0 * dscale;
+                ex = exp_neg(-sg * dd);
+                al = 1.0f - ex;
+                qf = 1.0f - al + 1e-10f;
+            }
+            // this sample's affine map y -> A + Q y, in double like the forward scan (and the reference's CPU cumsum)
+            double A = (double)dw * (double)al, Q = (double)qf;
+            // inclusive scan over the lanes: (A, Q) o (A', Q') = (A + Q A', Q Q')
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const double a2 = __shfl_up_sync(0xffffffffu, A, o), q2 = __shfl_up_sync(0xffffffffu, Q, o);
-                if (lane >= o) { A = fma(Q, a2, A); Q *= q2; }
+                const double a2s = __shfl_up_sync(0xffffffffu, A, o), q2s = __shfl_up_sync(0xffffffffu, Q, o);
+                if (lane >= o) { A = fma(Q, a2s, A); Q *= q2s; }
             }
-            const double zin = fma(Q, carry, A);     // Y in front of this lane's last (front-most) sample
+            const double zin = fma(Q, carry, A);     // Y in front of this lane's sample (includes it)
             double y = __shfl_up_sync(0xffffffffu, zin, 1);
-            if (lane == 0) y = carry;                // Y behind this lane's first sample
-#pragma unroll
-            for (int k = 0; k < KSB; ++k) {
-                if (jj[k] >= 0) {
-                    const float dalpha = (float)((double)tj[k] * ((double)dw[k] - y));
-                    const float dsigma = dalpha * dd[k] * ex[k];
-                    dsig[jj[k]] = dsigma * density_act_grad(xx[k], act);
-                    dn += dalpha * sg[k] * ex[k] * dd[k];      // d/d(norm) * norm
-                }
-                y = fma((double)qf[k], y, (double)dw[k] * (double)al[k]);
+            if (lane == 0) y = carry;                // Y_j: everything behind sample j
+            if (i < len) {
+                const float dalpha = (float)((double)tj0 * ((double)dw - y));
+                const float dsigma = dalpha * dd * ex;
+                dsig[j] = dsigma * density_act_grad(xx, act);
+                dn += dalpha * sg * ex * dd;          // d/d(norm) * norm
             }
             carry = __shfl_sync(0xffffffffu, zin, 31);
+            w0 = w1; sf0 = sf1; dj0 = dj1; tj0 = tj1; a0 = a1; c0 = c1;
+            w1 = w2; sf1 = sf2; dj1 = dj2; tj1 = tj2; a1 = a2;
         }
         if (dnorm) {
             dn = warp_sum(dn);

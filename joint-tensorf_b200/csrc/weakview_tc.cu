@@ -35,7 +35,8 @@ constexpr int INW = 100, K1W = 112;         // encoded input (reference order) /
 constexpr int BIASW1 = 20;
 constexpr int K2W = 48, K3W = 48;
 constexpr int MIDW = 44;                    // layer-3 input: PE(dir) 12 | h2 32 (tensorBase.py:209-212)
-constexpr int NT = TM;                      // threads per CTA
+constexpr int NT = TM;                      // threads per CTA of the backward data kernel (one per row)
+constexpr int NTF = 2 * TM;                 // forward: two threads per row (hh = tid >> 7 owns the chunks of its parity)
 
 // reference column (tensorBase.py:199-202 concatenation order) of A1 tile column c; -1 zero, -2 bias
 __host__ __device__ constexpr int ref_col_w1(int c) {
@@ -70,7 +71,7 @@ __device__ __forceinline__ void pe4(float x, float m0, float m1, float v[4]) {
 // comps [A][60] fp32 (jt_vm_gather_fwd app=1) -> rgb [A][4]; featdir [A][32] receives feat 0..19 and the view
 // direction at 28..30 (the backward's PE derivative needs the features, the fp32 layer-3 weights the direction).
 template <bool SAVE>
-__global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
+__global__ void __launch_bounds__(NTF) wv_head_fwd_kernel(const float* __restrict__ comps, const int* __restrict__ aidx,
                                                          const int* __restrict__ sidx, const float* __restrict__ rays_d,
                                                          int S, int normalize_dir, const float* __restrict__ Wb,
                                                          const float* __restrict__ W1, const float* __restrict__ b1,
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, r = tid;
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & (TM - 1), hh = tid >> 7;
     const int n = n_dev ? *n_dev : n_fixed;
     unsigned char* wb_hi = smem + L::off_wb;  unsigned char* wb_lo = wb_hi + L::WB;
     unsigned char* w1_hi = smem + L::off_w1;  unsigned char* w1_lo = w1_hi + L::W1;
@@ -102,13 +103,13 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
         return rc >= 0 ? W1[(size_t)j * INW + rc] : (rc == -2 ? b1[j] : 0.f);
     });
     stage_tile(w2_hi, w2_lo, HW, K2W, [&](int j, int k) { return k < HW ? W2[(size_t)j * HW + k] : (k == HW ? b2[j] : 0.f); });
-    for (int i = tid; i < 3 * MIDW + 3; i += NT) w3s[i] = i < 3 * MIDW ? W3[i] : b3[i - 3 * MIDW];
+    for (int i = tid; i < 3 * MIDW + 3; i += NTF) w3s[i] = i < 3 * MIDW ? W3[i] : b3[i - 3 * MIDW];
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t T_F = 0, T_H1 = 32, T_H2 = 64;
     uint32_t phase = 0;
     const float pf0 = fminf(fmaxf(fprog * 2.f - 0.f, 0.f), 1.f), pf1 = fminf(fmaxf(fprog * 2.f - 1.f, 0.f), 1.f);
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
             const float4* src = reinterpret_cast<const float4*>(comps + (size_t)(live ? row : 0) * C60);
 #pragma unroll
             for (int c = 0; c < KB / 8; ++c) {
+                if ((c & 1) != hh) continue;
                 float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
                 if (live) {
                     x = __ldcs(src + 2 * c);
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
         {
             float f[32];
             tmem_ld32(lane_addr + T_F, f);
-            if (live) {
+            if (live && hh == 0) {
                 float4* dst = reinterpret_cast<float4*>(featdir + (size_t)row * FD);
 #pragma unroll
                 for (int q = 0; q < FW / 4; ++q) __stcs(dst + q, make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]));
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
             }
 #pragma unroll
             for (int c = 0; c < K1W / 8; ++c) {
+                if ((c & 1) != hh) continue;
                 float v[8];
                 if (c < 3) {
 #pragma unroll
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
             tmem_ld32(lane_addr + T_H1, h);
 #pragma unroll
             for (int c = 0; c < K2W / 8; ++c) {
+                if ((c & 1) != hh) continue;
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -222,18 +226,20 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
             tmem_ld32(lane_addr + T_H2, h);
 #pragma unroll
             for (int e = 0; e < 3; ++e) pe4(dir[e], pv0, pv1, pd + 4 * e);
-            float o[3];
+            if (hh == 0) {                            // layer 3 + sigmoid: one thread of the pair
+                float o[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float s = w3s[3 * MIDW + c];
+                for (int c = 0; c < 3; ++c) {
+                    float s = w3s[3 * MIDW + c];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) s = fmaf(pd[k], w3s[c * MIDW + k], s);
+                    for (int k = 0; k < 12; ++k) s = fmaf(pd[k], w3s[c * MIDW + k], s);
 #pragma unroll
-                for (int j = 0; j < HW; ++j) s = fmaf(fmaxf(h[j], 0.f), w3s[c * MIDW + 12 + j], s);
-                o[c] = 1.f / (1.f + expf(-s));
+                    for (int j = 0; j < HW; ++j) s = fmaf(fmaxf(h[j], 0.f), w3s[c * MIDW + 12 + j], s);
+                    o[c] = 1.f / (1.f + expf(-s));
+                }
+                if (live) __stcs(reinterpret_cast<float4*>(rgb) + row, make_float4(o[0], o[1], o[2], 0.f));
             }
-            if (live) __stcs(reinterpret_cast<float4*>(rgb) + row, make_float4(o[0], o[1], o[2], 0.f));
-            if (SAVE) {
+            if (SAVE && hh == 1) {                    // ... the other one writes the A3 tile
                 float row3[K3W];                      // relu(h2) 32 | PE(dir) 12 | 1 | 0 0 0
 #pragma unroll
                 for (int j = 0; j < HW; ++j) row3[j] = fmaxf(h[j], 0.f);
@@ -242,8 +248,8 @@ __global__ void __launch_bounds__(NT) wv_head_fwd_kernel(const float* __restrict
                 row3[HW + 12] = 1.f; row3[HW + 13] = row3[HW + 14] = row3[HW + 15] = 0.f;
 #pragma unroll
                 for (int c = 0; c < K3W / 8; ++c) store_chunk(a3, nullptr, TM, c, r, row3 + 8 * c);
-                fence_async_smem();
             }
+            if (SAVE) fence_async_smem();
         }
         tc_fence_before();               // all tcgen05.ld of this tile are complete before the next tile's MMAs
         __syncthreads();
@@ -600,12 +606,12 @@ extern "C" int jt_wv_head_fwd_tc(const float* comps, const int* aidx, const int*
     unsigned char* st = static_cast<unsigned char*>(stage);
     if (st) {
         if (int rc = set_smem(wv_head_fwd_kernel<true>, FwdSmem::total)) return rc;
-        wv_head_fwd_kernel<true><<<grid, NT, FwdSmem::total, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1, b1,
+        wv_head_fwd_kernel<true><<<grid, NTF, FwdSmem::total, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1, b1,
                                                                       W2, b2, W3, b3, n_dev, n_max, fea_progress, view_progress,
                                                                       featdir, rgb, st);
     } else {
         if (int rc = set_smem(wv_head_fwd_kernel<false>, FwdSmem::total)) return rc;
-        wv_head_fwd_kernel<false><<<grid, NT, FwdSmem::total, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1, b1,
+        wv_head_fwd_kernel<false><<<grid, NTF, FwdSmem::total, stream>>>(comps, aidx, sidx, rays_d, n_samples, normalize_dir, Wb, W1, b1,
                                                                        W2, b2, W3, b3, n_dev, n_max, fea_progress, view_progress,
                                                                        featdir, rgb, nullptr);
     }

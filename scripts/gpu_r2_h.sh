@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, call H (1 GPU): parity after the double-precision / 4-samples-per-lane compositing kernels + bench lines.
 mkdir -p gpurun_out
-TAG=${TAG:-r02h}
+TAG=${TAG:-r02k}
 rm -f gpurun_out/parity_errors.jsonl
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/${TAG}_gpu_tests.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${TAG}_gpu_tests.log

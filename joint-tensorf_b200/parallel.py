@@ -85,12 +85,12 @@ class OverlappedGradSync:
         seeded differently.
     World size 1: every call is a no-op."""
 
-    def __init__(self, group=None, per_plane=False, reserve_sms=0, split21=True):
+    def __init__(self, group=None, per_plane=False, reserve_sms=0, split21=False):
         self.group = group
         self.works = []
         self.bytes = 0
         self.enabled = True
-        self.split21 = split21            # default: planes 0+1 | plane 2 | density, a collective after each (render.py)
+        self.split21 = split21            # variant: planes 0+1 | plane 2 | density, a collective after each (render.py)
         self.per_plane = per_plane        # one scatter launch + all-reduce per appearance plane (render.py)
         self.reserve_sms = reserve_sms    # SMs the density scatter leaves to the collective running next to it
 

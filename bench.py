@@ -62,8 +62,9 @@ def parse():
                     help="capture the step (pose -> rays -> forward -> loss -> backward [-> all-reduce]) into a CUDA graph "
                          "and replay it: removes the ~1.4 ms of host launch time that bounds small / strong-scaled batches")
     ap.add_argument("--sync-per-plane", action="store_true", help="N > 1: one scatter launch + all-reduce per appearance plane")
-    ap.add_argument("--sync-split21", action="store_true",
-                    help="N > 1: appearance planes 0+1 | plane 2 | density, a collective after each launch")
+    ap.add_argument("--sync-split21", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: appearance planes 0+1 | plane 2 | density, a collective after each launch (auto: 4+ ranks "
+                         "and an appearance-dominated gradient bucket)")
     ap.add_argument("--sync-reserve-sms", type=int, default=0,
                     help="N > 1: SMs the density scatter leaves free for the all-reduce running next to it")
     ap.add_argument("--storage", default="fp32", choices=["fp32", "bf16"],
@@ -520,7 +521,7 @@ def own_arm(args):
     # data parallel: the render node's backward reduces its flat gradient bucket across ranks itself (appearance
     # part overlapped with the density scatter); the loss carries the 1/world factor, so the sums are means
     sync = (parallel.OverlappedGradSync(per_plane=args.sync_per_plane, reserve_sms=args.sync_reserve_sms,
-                                        split21=args.sync_split21)
+                                        split21={"auto": "auto", "on": True, "off": False}[args.sync_split21])
             .attach(model, [se3_refine]) if world > 1 else None)
     inv_world = 1.0 / world
 

@@ -85,14 +85,22 @@ class OverlappedGradSync:
         seeded differently.
     World size 1: every call is a no-op."""
 
-    def __init__(self, group=None, per_plane=False, reserve_sms=0, split21=False):
+    def __init__(self, group=None, per_plane=False, reserve_sms=0, split21="auto"):
         self.group = group
         self.works = []
         self.bytes = 0
         self.enabled = True
-        self.split21 = split21            # variant: planes 0+1 | plane 2 | density, a collective after each (render.py)
+        # planes 0+1 | plane 2 | density with a collective after each launch (render.py). "auto": when it pays --
+        # 4 or more ranks and an appearance part that dominates the bucket (measured: N=8 cfg2_sh 3.21 -> 3.12 ms,
+        # N=2 3.04 -> 3.04, N=2 cfg4 2.15 -> 2.29)
+        self.split21 = split21
         self.per_plane = per_plane        # one scatter launch + all-reduce per appearance plane (render.py)
         self.reserve_sms = reserve_sms    # SMs the density scatter leaves to the collective running next to it
+
+    def use_split21(self, n_app, n_total):
+        if self.split21 == "auto":
+            return dist.get_world_size(self.group) >= 4 and n_app >= 2 * (n_total - n_app)
+        return bool(self.split21)
 
     def _active(self):
         return self.enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1

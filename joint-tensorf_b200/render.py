@@ -393,15 +393,16 @@ class VMRender(torch.autograd.Function):
             ops.vm_scatter_rays(0, dfs, gdp, gdl, comp.samp, None, comp.sidx, comp.count, cap_v, dsig, cfg.n_samples,
                                 cfg.h_inv, d_o, d_d, max_ctas=-80)
             sync.on_rest(flat[n_app:])
-        elif getattr(sync, "split21", False):
-            # data-parallel variant: [appearance planes 0+1: one persistent launch] -> all-reduce of their 2/4 of the
+        elif sync.use_split21(n_app, flat.numel()):
+            # data parallel, 4+ ranks with an appearance-dominated bucket: [appearance planes 0+1: one persistent launch] -> all-reduce of their 2/4 of the
             # bucket starts -> [appearance plane 2] -> all-reduce of plane 2 + the three lines -> [density scatter] ->
             # all-reduce of the rest. The collectives get a 0.7 ms window (plane 2 + density) instead of the 0.4 ms of the
             # density scatter alone, which at N = 8 is shorter than the 69 MB all-reduce itself; the two launches that run
             # next to a collective use fixed 80-sample segments on a non-persistent grid, because NCCL's CTAs can only
             # get onto an SM when scatter CTAs retire (a persistent wave holds every SM until its kernel ends).
-            # Measured at N = 2 (profiles/r02l_*): the exposed wait halves (0.20 -> 0.09 ms) and the two scatters that
-            # share the SMs with a collective lose as much (+0.03, +0.06 ms): 3.038 vs 3.041 ms; cfg4 gets slower.
+            # Measured (profiles/r02l_*, r02n8c_*): N = 8: exposed wait 0.36 -> 0.16 ms, the two scatters that share the
+            # SMs with a collective lose 0.10 ms, step 3.21 -> 3.12 ms; N = 2: 3.04 vs 3.04 ms; cfg4 at N = 2 gets slower
+            # (2.15 -> 2.29: its bucket is half density) -- hence OverlappedGradSync.use_split21.
             ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
                                 cfg.n_samples, cfg.h_inv, d_o, d_d, plane_mask=3)
             n01 = sizes[0] + sizes[1]
@@ -415,7 +416,7 @@ class VMRender(torch.autograd.Function):
             # them to p.grad, clone them, feed the adjoint blur) sees the cross-rank sums
             sync.on_rest(flat[n_app:])
         else:
-            # default: the appearance part of the bucket (3/4 of the bytes) is all-reduced while the density
+            # 2 ranks / density-heavy buckets: the appearance part of the bucket is all-reduced while the density
             # scatter runs (non-persistent grid, or a persistent wave that leaves sync.reserve_sms SMs to the collective)
             ops.vm_scatter_rays(1, afs, gap, gal, comp.samp, b["aidx"], comp.sidx, b["a_count"], cap, dcomps,
                                 cfg.n_samples, cfg.h_inv, d_o, d_d)

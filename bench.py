@@ -543,8 +543,6 @@ def own_arm(args):
     step = make_step(model, opt, params)
     eager_step = step
     launches_per_graph = None
-    if args.cuda_graph and world > 1:
-        raise SystemExit("--cuda-graph: the data-parallel step (NCCL all-reduces inside autograd) is not captured; N = 1 only")
     if args.cuda_graph:
         # the whole step as ONE graph launch: static input buffers refreshed in place, static loss / gradients
         model.app_capacity = None                    # the automatic capacity tracker polls events: not capturable
@@ -943,6 +941,13 @@ def own_arm(args):
         if extras is not None:
             line["next_rows"] = extras
         print(json.dumps(line), flush=True)
+    if world > 1 and args.cuda_graph:
+        # a process group whose collectives were captured into a live CUDA graph does not tear down cleanly
+        # (destroy_process_group hung at N = 2): synchronise, meet the other ranks, leave without the teardown
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
 

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 import joint_tensorf_b200 as jt
-from common import GOLDEN_DIR, rel_err, vo
+from common import GOLDEN_DIR, vo
 from joint_tensorf_b200.options import Namespace
 from oracle import field_oracle as fo
 

@@ -99,3 +99,48 @@ def test_gradient_bucket_allreduce_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret[0] and ret[1]
+
+
+class _TinyModel(torch.nn.Module):
+    def __init__(self, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        # a channel-last factor (as B200_VMSplit stores them) and a dense weight, DIFFERENT on every rank
+        p = torch.randn(1, 4, 3, 5, generator=g)
+        self.plane = torch.nn.Parameter(p.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+        self.w = torch.nn.Parameter(torch.randn(3, 2, generator=g))
+        self.grad_sync = None
+
+
+def _worker_attach(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = _TinyModel(seed=10 + rank)
+    se3 = torch.nn.Parameter(torch.full((2, 6), float(rank)))
+    ref = _TinyModel(seed=10)                                  # what rank 0 holds
+    sync = parallel.OverlappedGradSync().attach(m, [se3])
+    ok = m.grad_sync is sync and torch.equal(m.plane, ref.plane) and torch.equal(m.w, ref.w) and \
+        torch.equal(se3, torch.zeros(2, 6)) and m.plane.stride() == ref.plane.stride()
+    # paused(): no collective is issued (a rank-local backward must not wait for the other ranks)
+    flat = torch.full((6,), float(rank + 1))
+    with sync.paused():
+        sync.on_app_grads(flat[:3])
+        sync.on_rest(flat[3:])
+        sync.finish([se3])
+    ok = ok and torch.equal(flat, torch.full((6,), float(rank + 1))) and sync._active()
+    # the split-backward policy: 2 ranks -> single launch; forced on / off
+    ok = ok and not sync.use_split21(90, 100)
+    ok = ok and parallel.OverlappedGradSync(split21=True).use_split21(10, 100)
+    ok = ok and not parallel.OverlappedGradSync(split21=False).use_split21(90, 100)
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_attach_broadcasts_and_paused_skips_collectives_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_attach, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret[0] and ret[1]

@@ -149,3 +149,23 @@ def test_image_oracle_matches_reference_golden():
         assert torch.allclose(d, l["d_rgb"], rtol=1e-6, atol=1e-9, equal_nan=True), l["tag"]
     v = g["loss_val"]
     assert abs(float(io.render_loss(v["rgb"], images, None, None, 0, 1.5, 0.5)) - float(v["loss"])) <= 1e-7
+
+
+@pytest.mark.parametrize("name", ["cubic_mlp", "sh_vm48", "ndc_weakview_blur"])
+def test_float64_yardstick_mode_tracks_the_reference(name):
+    """vo.render(exact=True): samples placed in fp32 exactly as the reference does (same valid mask, same appearance
+    set), everything downstream in float64. The GPU tests use it to tell the reference's own fp32 rounding from a real
+    discrepancy on ill-conditioned full-size gradients; here it must agree with the reference's fp32 outputs to fp32
+    rounding on the well-conditioned golden cases."""
+    g = load_golden(name)
+    f64 = field_from_golden(g)
+    f64.params = {k: v.detach().double().requires_grad_(True) for k, v in f64.params.items()}
+    o, d = g["rays_o"].clone().requires_grad_(True), g["rays_d"].clone().requires_grad_(True)
+    rgb, depth, acc, det = vo.render(f64, o, d, exact=True, detail=True, **render_kwargs_from_golden(g))
+    assert rgb.dtype == torch.float64
+    assert torch.equal(det["valid"], golden_valid(g))
+    assert (rgb.float() - g["rgb"]).abs().max() <= 2e-6 and (acc.float() - g["acc"]).abs().max() <= 2e-6
+    ((rgb * g["w_rgb"]).sum() + (acc * g["w_acc"]).sum()).backward()
+    assert rel_err(o.grad, g["d_rays_o"]) <= 1e-4
+    for k, ref in g["grads"].items():
+        assert rel_err(f64.params[k].grad.float(), ref) <= 1e-4, k
